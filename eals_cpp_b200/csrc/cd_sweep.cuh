@@ -1,0 +1,269 @@
+// cd_sweep.cuh — K1: the per-row coordinate-descent sweep of eALS.
+//
+// Replaces MF_fastALS::update_user_thread (MF_fastALS.cpp:243-322) and update_item_thread
+// (:338-407).  For one row (a user, or an item on the transposed side) with nonzeros j = 1..n over
+// neighbour rows y_j of the OTHER factor matrix, and the frozen S cache of the other side:
+//
+//   pred_j = <x, y_j>                                                      (:261-270 / :352-363)
+//   for f = 0..K-1 (sequential — each step sees the factors updated before it):
+//     numer = -g * sum_{k != f} x_k S[f][k]          g = 1 (user) | Wi[row] (item)   (:284-287 / :375-380)
+//     pred_j -= x_f y_jf ; numer += (w_j r_j - c_j pred_j) y_jf ; denom += c_j y_jf^2     (:297-305 / :385-390)
+//     denom += g S[f][f] + reg ;  x_f = numer / denom ; pred_j += x_f y_jf            (:307-315 / :391-400)
+//   with c_j = w_j - Wi[item] (item = neighbour j on the user side, the row itself on the item side).
+//
+// Rows are independent inside a half-epoch (they only read the other side's factors, its S cache
+// and Wi), so they are spread over warps / CTAs in any order; only the floating-point summation
+// order over j differs from the reference's sequential loop.
+//
+// Data movement.  The n x K tile of gathered neighbour rows is what the K steps walk column by
+// column.  It is staged through shared memory one 128-byte factor block (16 doubles of every
+// gathered row = one full cache line each) at a time, so global memory sees whole lines exactly
+// once per pass; the per-nonzero prediction cache lives in registers (warp kernel) or in a
+// device-resident fp64 array (CTA kernel, rows of any length).
+#pragma once
+
+#include "common.cuh"
+
+namespace eals {
+
+struct CdSide {
+  const int64_t* ptr;   // [rows+1] offsets of the owned rows (first owned row at 0)
+  const int32_t* idx;   // neighbour ids, ascending inside a row
+  const double* val;    // rating (= confidence weight) per nonzero, or nullptr for all-ones
+  double* X;            // factors being updated, full replica [n][LD]
+  const double* Y;      // the other side's factors [n'][LD]
+  const double* S;      // the other side's S cache [K][LD]
+  const double* Wi;     // item popularity weights [n_items]
+  int row_base;         // global id of owned row 0
+  int K;
+  double reg;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-row kernel: rows with 1..32*MAXM nonzeros.  Lane l owns nonzeros l, l+32, ...; their
+// prediction cache, weights and the current column value stay in registers.  Per factor: one
+// shared-memory column read per owned nonzero, a K/32-long slice of the S-row dot product, one
+// paired warp reduction (numerator, denominator), one fp64 divide.
+// ---------------------------------------------------------------------------------------------
+template <int LD, int MAXM>
+struct CdWarpSmem {
+  static constexpr int kRows = 32 * MAXM;
+  static constexpr int kBytesPerWarp = kRows * kTilePad * 8 + LD * 8 + kRows * 4;
+};
+
+template <int LD, int MAXM>
+__device__ __forceinline__ void stage_block(double* tile, const int* idx_s, const double* __restrict__ Y,
+                                            int n, int fb) {
+  const int lane = lane_id();
+  const int n8 = n * 8;  // 16-byte chunks in this block: 8 per gathered row
+  for (int t0 = lane; t0 < n8; t0 += 128) {
+    double2 d[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int t = t0 + q * 32;
+      if (t < n8) d[q] = ldg2(Y + (size_t)idx_s[t >> 3] * LD + fb * kFB + (t & 7) * 2);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int t = t0 + q * 32;
+      if (t < n8) {
+        double* dst = tile + (t >> 3) * kTilePad + (t & 7) * 2;
+        dst[0] = d[q].x;
+        dst[1] = d[q].y;
+      }
+    }
+  }
+}
+
+template <int LD, int MAXM, bool USER>
+__global__ void __launch_bounds__(128)
+cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Sm = CdWarpSmem<LD, MAXM>;
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (slot >= count) return;  // warp-uniform; no block-wide barrier is used below
+
+  double* tile = reinterpret_cast<double*>(smem_raw + (size_t)warp * Sm::kBytesPerWarp);
+  double* u_s = tile + Sm::kRows * kTilePad;
+  int* idx_s = reinterpret_cast<int*>(u_s + LD);
+
+  const int row = order[first + slot];
+  const int64_t p0 = a.ptr[row];
+  const int n = (int)(a.ptr[row + 1] - p0);
+  const int grow = a.row_base + row;
+  double* xrow = a.X + (size_t)grow * LD;
+  const int K = a.K;
+  const double wi_row = USER ? 0.0 : a.Wi[grow];
+
+  for (int k = lane; k < LD; k += 32) u_s[k] = xrow[k];
+
+  double wr[MAXM], cw[MAXM], pr[MAXM], vv[MAXM];
+  bool ok[MAXM];
+#pragma unroll
+  for (int m = 0; m < MAXM; m++) {
+    const int j = m * 32 + lane;
+    ok[m] = j < n;
+    wr[m] = cw[m] = pr[m] = vv[m] = 0.0;
+    if (ok[m]) {
+      const int id = a.idx[p0 + j];
+      idx_s[j] = id;
+      const double w = a.val ? a.val[p0 + j] : 1.0;
+      wr[m] = w * w;                                   // w_ui * r_ui, both are the stored value
+      cw[m] = w - (USER ? a.Wi[id] : wi_row);
+    }
+  }
+  __syncwarp();
+
+  const int nblocks = (K + kFB - 1) / kFB;
+
+  // Pass 1: prediction cache  pred_j = <x, y_j>, accumulated in factor order.
+  for (int fb = 0; fb < nblocks; fb++) {
+    stage_block<LD, MAXM>(tile, idx_s, a.Y, n, fb);
+    __syncwarp();
+#pragma unroll
+    for (int fl = 0; fl < kFB; fl++) {
+      const double uf = u_s[fb * kFB + fl];
+#pragma unroll
+      for (int m = 0; m < MAXM; m++)
+        if (ok[m]) pr[m] += uf * tile[(m * 32 + lane) * kTilePad + fl];
+    }
+    __syncwarp();
+  }
+
+  // Pass 2: the K sequential coordinate updates.
+  for (int fb = 0; fb < nblocks; fb++) {
+    stage_block<LD, MAXM>(tile, idx_s, a.Y, n, fb);
+    __syncwarp();
+    const int fend = min(kFB, K - fb * kFB);
+    for (int fl = 0; fl < fend; fl++) {
+      const int f = fb * kFB + fl;
+      const double uf = u_s[f];
+      const double* __restrict__ Srow = a.S + (size_t)f * LD;
+      double np = 0.0, dp = 0.0;
+      for (int k = lane; k < K; k += 32)
+        if (k != f) np -= u_s[k] * __ldg(Srow + k);
+      if (!USER) np *= wi_row;
+#pragma unroll
+      for (int m = 0; m < MAXM; m++) {
+        if (ok[m]) {
+          const double v = tile[(m * 32 + lane) * kTilePad + fl];
+          const double pm = pr[m] - uf * v;
+          np += (wr[m] - cw[m] * pm) * v;
+          dp += cw[m] * v * v;
+          pr[m] = pm;
+          vv[m] = v;
+        }
+      }
+      warp_sum_pair(np, dp);
+      const double sff = __ldg(Srow + f);
+      dp += (USER ? sff : wi_row * sff) + a.reg;
+      const double unew = np / dp;
+#pragma unroll
+      for (int m = 0; m < MAXM; m++)
+        if (ok[m]) pr[m] += unew * vv[m];
+      __syncwarp();
+      if (lane == 0) u_s[f] = unew;
+      __syncwarp();
+    }
+  }
+  for (int k = lane; k < K; k += 32) xrow[k] = u_s[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-per-row kernel: rows of ANY length.  The prediction cache is a device-resident fp64 array
+// `e` (one slot per nonzero of the owned rows); every factor step streams the row once, reading
+// the two adjacent factor columns f-1 and f of each gathered row (same 32-byte sector three times
+// out of four) so the cache refresh of step f-1 is folded into step f.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCtaThreads = 256;
+
+template <int LD, bool USER>
+__global__ void __launch_bounds__(kCtaThreads)
+cd_cta_kernel(CdSide a, const int32_t* __restrict__ order, int first,
+              const int64_t* __restrict__ long_ptr, double* __restrict__ e) {
+  __shared__ double u_s[LD];
+  __shared__ double red[2][kCtaThreads / 32][2];
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+
+  const int row = order[first + blockIdx.x];
+  const int64_t p0 = a.ptr[row];
+  const int n = (int)(a.ptr[row + 1] - p0);
+  const int grow = a.row_base + row;
+  double* xrow = a.X + (size_t)grow * LD;
+  const int K = a.K;
+  const double wi_row = USER ? 0.0 : a.Wi[grow];
+  const int32_t* __restrict__ idx = a.idx + p0;
+  const double* __restrict__ val = a.val ? a.val + p0 : nullptr;
+  double* __restrict__ er = e + long_ptr[row];
+
+  for (int k = tid; k < LD; k += kCtaThreads) u_s[k] = xrow[k];
+  __syncthreads();
+
+  // Prediction cache: 8 lanes per nonzero, each reading 16 B of every 128 B line of the row.
+  {
+    const int g = tid >> 3, gl = tid & 7;
+    for (int j0 = 0; j0 < n; j0 += kCtaThreads / 8) {
+      const int j = j0 + g;
+      double acc = 0.0;
+      if (j < n) {
+        const double* yrow = a.Y + (size_t)idx[j] * LD;
+#pragma unroll
+        for (int c = 0; c < LD; c += kFB) {
+          const double2 d = ldg2(yrow + c + gl * 2);
+          acc += u_s[c + gl * 2] * d.x;
+          acc += u_s[c + gl * 2 + 1] * d.y;
+        }
+      }
+      acc += __shfl_xor_sync(kFullMask, acc, 1);
+      acc += __shfl_xor_sync(kFullMask, acc, 2);
+      acc += __shfl_xor_sync(kFullMask, acc, 4);
+      if (j < n && gl == 0) er[j] = acc;
+    }
+  }
+  __syncthreads();
+
+  double pend = 0.0;  // x_{f-1} just computed: its cache refresh is applied while streaming step f
+  for (int f = 0; f < K; f++) {
+    const double uf = u_s[f];
+    const double* __restrict__ Srow = a.S + (size_t)f * LD;
+    double np = 0.0, dp = 0.0;
+    for (int k = tid; k < K; k += kCtaThreads)
+      if (k != f) np -= u_s[k] * __ldg(Srow + k);
+    if (!USER) np *= wi_row;
+    for (int j = tid; j < n; j += kCtaThreads) {
+      const int id = idx[j];
+      const double* yrow = a.Y + (size_t)id * LD;
+      const double v = __ldg(yrow + f);
+      double pm = er[j];
+      if (f > 0) pm += pend * __ldg(yrow + f - 1);
+      pm -= uf * v;
+      const double w = val ? val[j] : 1.0;
+      const double c = w - (USER ? __ldg(a.Wi + id) : wi_row);
+      np += (w * w - c * pm) * v;
+      dp += c * v * v;
+      er[j] = pm;
+    }
+    warp_sum_pair(np, dp);
+    if (lane == 0) {
+      red[f & 1][warp][0] = np;
+      red[f & 1][warp][1] = dp;
+    }
+    __syncthreads();
+    double numer = 0.0, denom = 0.0;
+#pragma unroll
+    for (int w = 0; w < kCtaThreads / 32; w++) {
+      numer += red[f & 1][w][0];
+      denom += red[f & 1][w][1];
+    }
+    const double sff = __ldg(Srow + f);
+    denom += (USER ? sff : wi_row * sff) + a.reg;
+    const double unew = numer / denom;
+    pend = unew;
+    if (tid == 0) u_s[f] = unew;
+    __syncthreads();
+  }
+  for (int k = tid; k < K; k += kCtaThreads) xrow[k] = u_s[k];
+}
+
+}  // namespace eals

@@ -1,0 +1,973 @@
+// eals_b200.cu — libeals_b200.so: the C ABI of include/eals_b200.h over the sm_100a kernels in this
+// directory.  Host-side logic here is limited to what the reference's constructor does once
+// (popularity weights, factor initialisation — both on the host with the SAME libm / libstdc++
+// calls as the reference, so they are bit-identical by construction), row bucketing by length,
+// launch sequencing, and the replay of the reference's int-truncating partial_sort_copy for the
+// few users that survive the count-larger filter in evaluation.
+//
+// There is no CPU compute fallback: every entry point that does work needs a CUDA device.
+
+#include "../../include/eals_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <random>
+#include <utility>
+#include <vector>
+
+#include "cd_sweep.cuh"
+#include "common.cuh"
+#include "eval.cuh"
+#include "gram.cuh"
+#include "loss.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(e_ == cudaErrorMemoryAllocation ? EALS_ERR_ALLOC : EALS_ERR_CUDA,              \
+                  "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));          \
+  } while (0)
+
+#define OK(call)                 \
+  do {                           \
+    int r_ = (call);             \
+    if (r_ != EALS_OK) return r_; \
+  } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CU(cudaMalloc((void**)p, n * sizeof(T)));
+  return EALS_OK;
+}
+
+// Buckets of owned rows by length.  Bucket 0 = empty rows (skipped: MF_fastALS.cpp:249,344).
+constexpr int kNumBuckets = 5;
+constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 128, 0x7fffffff};
+constexpr int kLongBucket = 4;
+
+struct Side {
+  int rows = 0;       // owned rows
+  int row_base = 0;   // global id of owned row 0
+  int64_t nnz = 0;    // nonzeros of the owned rows
+  int64_t* ptr = nullptr;
+  int32_t* idx = nullptr;
+  double* val = nullptr;
+  int32_t* order = nullptr;           // owned-row ids grouped by bucket, ascending id inside
+  int first[kNumBuckets + 1] = {0};   // bucket b = order[first[b] .. first[b+1])
+  int64_t* long_ptr = nullptr;        // ptr rebased so that long rows index a compact pred cache
+  int64_t long_nnz = 0;
+  double* pred = nullptr;             // prediction cache of the long rows
+  std::vector<int64_t> h_ptr;         // host copy of ptr (rebased to 0)
+};
+
+enum { T_USER_SWEEP, T_USER_GRAM, T_ITEM_SWEEP, T_ITEM_GRAM, T_LOSS, T_EVAL, T_COUNT };
+
+}  // namespace
+
+struct eals_model {
+  eals_params p;
+  cudaStream_t own_stream = nullptr;
+  int K = 0, LD = 0;
+  int M = 0, N = 0;
+  int ub = 0, ue = 0, ib = 0, ie = 0;
+  cudaStream_t stream = nullptr;
+  double *U = nullptr, *V = nullptr, *SU = nullptr, *SV = nullptr, *Wi = nullptr;
+  double* terms = nullptr;      // [4] loss terms
+  double* partials = nullptr;   // scratch for deterministic two-stage reductions
+  size_t partials_len = 0;
+  Side users, items;
+  int sm_count = 148;
+  int64_t launches = 0;
+  cudaEvent_t ev[T_COUNT][2];
+  bool timed[T_COUNT];
+  bool factors_set = false;
+};
+
+namespace {
+
+using eals::CdSide;
+
+int sync_if_debug(eals_model* m) {
+  if (m->p.flags & EALS_FLAG_SYNC_EACH_CALL) {
+    CU(cudaStreamSynchronize(m->stream));
+    CU(cudaGetLastError());
+  }
+  return EALS_OK;
+}
+
+int check_launch(eals_model* m) {
+  m->launches++;
+  CU(cudaGetLastError());
+  return EALS_OK;
+}
+
+void free_side(Side& s) {
+  cudaFree(s.ptr); cudaFree(s.idx); cudaFree(s.val); cudaFree(s.order);
+  cudaFree(s.long_ptr); cudaFree(s.pred);
+  s = Side();
+}
+
+// Copy `n` elements from a host or device source to a device destination.
+template <typename T>
+int copy_in(T* dst, const T* src, size_t n, int space, cudaStream_t st) {
+  if (n == 0) return EALS_OK;
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(T),
+                     space == EALS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  return EALS_OK;
+}
+
+__global__ void check_sorted_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                    int rows, int limit, int* __restrict__ bad) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int prev = -1;
+  for (int64_t p = ptr[r]; p < ptr[r + 1]; p++) {
+    const int c = idx[p];
+    if (c <= prev || c >= limit) { atomicExch(bad, 1); return; }
+    prev = c;
+  }
+}
+
+// Upload the owned slice [begin, end) of one orientation of the matrix and bucket its rows.
+int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int space,
+               const int64_t* ptr_full, const int32_t* idx_full, const double* val_full) {
+  free_side(s);
+  s.rows = end - begin;
+  s.row_base = begin;
+  s.h_ptr.assign((size_t)s.rows + 1, 0);
+  if (s.rows > 0) {
+    if (space == EALS_DEVICE) {
+      CU(cudaMemcpy(s.h_ptr.data(), ptr_full + begin, sizeof(int64_t) * (s.rows + 1), cudaMemcpyDeviceToHost));
+    } else {
+      std::memcpy(s.h_ptr.data(), ptr_full + begin, sizeof(int64_t) * (s.rows + 1));
+    }
+  }
+  const int64_t base = s.h_ptr[0];
+  for (auto& v : s.h_ptr) v -= base;
+  for (int r = 0; r < s.rows; r++)
+    if (s.h_ptr[r + 1] < s.h_ptr[r] || s.h_ptr[r + 1] - s.h_ptr[r] > other_dim)
+      return fail(EALS_ERR_ARG, "offsets not monotone / row longer than the other dimension at row %d", begin + r);
+  s.nnz = s.h_ptr[s.rows];
+
+  OK(dev_alloc(&s.ptr, (size_t)s.rows + 1));
+  OK(dev_alloc(&s.idx, (size_t)s.nnz));
+  CU(cudaMemcpyAsync(s.ptr, s.h_ptr.data(), sizeof(int64_t) * (s.rows + 1), cudaMemcpyHostToDevice, m->stream));
+  OK(copy_in(s.idx, idx_full + base, (size_t)s.nnz, space, m->stream));
+  if (val_full) {
+    OK(dev_alloc(&s.val, (size_t)s.nnz));
+    OK(copy_in(s.val, val_full + base, (size_t)s.nnz, space, m->stream));
+  }
+
+  // indices must ascend strictly inside a row and stay in range (main.cpp:198-205 order)
+  if (s.rows > 0) {
+    int* bad;
+    OK(dev_alloc(&bad, 1));
+    CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
+    check_sorted_kernel<<<(s.rows + 255) / 256, 256, 0, m->stream>>>(s.ptr, s.idx, s.rows, other_dim, bad);
+    OK(check_launch(m));
+    int h_bad = 0;
+    CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    cudaFree(bad);
+    if (h_bad) return fail(EALS_ERR_ARG, "indices inside a row must be strictly ascending and in range");
+  }
+
+  // counting sort of the rows into length buckets
+  std::vector<int32_t> order((size_t)std::max(s.rows, 1));
+  int count[kNumBuckets] = {0};
+  auto bucket_of = [](int64_t n) {
+    int b = 0;
+    while (n > kBucketMax[b]) b++;
+    return b;
+  };
+  for (int r = 0; r < s.rows; r++) count[bucket_of(s.h_ptr[r + 1] - s.h_ptr[r])]++;
+  s.first[0] = 0;
+  for (int b = 0; b < kNumBuckets; b++) s.first[b + 1] = s.first[b] + count[b];
+  int fill[kNumBuckets];
+  for (int b = 0; b < kNumBuckets; b++) fill[b] = s.first[b];
+  for (int r = 0; r < s.rows; r++) order[fill[bucket_of(s.h_ptr[r + 1] - s.h_ptr[r])]++] = r;
+  // long rows: longest first, so the tail of the launch is made of the cheapest rows
+  std::stable_sort(order.begin() + s.first[kLongBucket], order.begin() + s.first[kLongBucket + 1],
+                   [&](int a, int b) {
+                     return s.h_ptr[a + 1] - s.h_ptr[a] > s.h_ptr[b + 1] - s.h_ptr[b];
+                   });
+  OK(dev_alloc(&s.order, order.size()));
+  CU(cudaMemcpyAsync(s.order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, m->stream));
+
+  // compact prediction cache for the long rows
+  std::vector<int64_t> long_ptr((size_t)s.rows + 1, 0);
+  int64_t acc = 0;
+  for (int r = 0; r < s.rows; r++) {
+    const int64_t n = s.h_ptr[r + 1] - s.h_ptr[r];
+    long_ptr[r] = acc;
+    if (n > kBucketMax[kLongBucket - 1]) acc += n;
+  }
+  long_ptr[s.rows] = acc;
+  s.long_nnz = acc;
+  OK(dev_alloc(&s.long_ptr, long_ptr.size()));
+  CU(cudaMemcpyAsync(s.long_ptr, long_ptr.data(), sizeof(int64_t) * long_ptr.size(), cudaMemcpyHostToDevice, m->stream));
+  OK(dev_alloc(&s.pred, (size_t)s.long_nnz));
+  CU(cudaStreamSynchronize(m->stream));
+  return EALS_OK;
+}
+
+// Wi — MF_fastALS.cpp:55-72, on the host with the same libm pow and the same summation order.
+int compute_item_weights(eals_model* m, int space, const int64_t* col_ptr_full) {
+  const int N = m->N;
+  std::vector<int64_t> cp((size_t)N + 1);
+  if (space == EALS_DEVICE) {
+    CU(cudaMemcpy(cp.data(), col_ptr_full, sizeof(int64_t) * (N + 1), cudaMemcpyDeviceToHost));
+  } else {
+    std::memcpy(cp.data(), col_ptr_full, sizeof(int64_t) * (N + 1));
+  }
+  std::vector<double> p((size_t)N);
+  double sum = 0, Z = 0;
+  for (int i = 0; i < N; i++) {
+    p[i] = (double)(int)(cp[i + 1] - cp[i]);
+    sum += p[i];
+  }
+  for (int i = 0; i < N; i++) {
+    p[i] /= sum;
+    p[i] = pow(p[i], m->p.alpha);
+    Z += p[i];
+  }
+  for (int i = 0; i < N; i++) p[i] = m->p.w0 * p[i] / Z;
+  CU(cudaMemcpyAsync(m->Wi, p.data(), sizeof(double) * N, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return EALS_OK;
+}
+
+int ensure_partials(eals_model* m, size_t n) {
+  if (n <= m->partials_len) return EALS_OK;
+  cudaFree(m->partials);
+  m->partials = nullptr;
+  m->partials_len = 0;
+  OK(dev_alloc(&m->partials, n));
+  m->partials_len = n;
+  return EALS_OK;
+}
+
+void tic(eals_model* m, int which) { cudaEventRecord(m->ev[which][0], m->stream); }
+void toc(eals_model* m, int which) {
+  cudaEventRecord(m->ev[which][1], m->stream);
+  m->timed[which] = true;
+}
+
+// ---- dispatch on the leading dimension (16, 32, 64, 128, 256) ---------------------------------
+#define DISPATCH_LD(LDV, ...)                                              \
+  switch (LDV) {                                                           \
+    case 16: { constexpr int LD = 16; __VA_ARGS__; } break;                \
+    case 32: { constexpr int LD = 32; __VA_ARGS__; } break;                \
+    case 64: { constexpr int LD = 64; __VA_ARGS__; } break;                \
+    case 128: { constexpr int LD = 128; __VA_ARGS__; } break;              \
+    case 256: { constexpr int LD = 256; __VA_ARGS__; } break;              \
+    default: return fail(EALS_ERR_UNSUPPORTED, "leading dimension %d", LDV); \
+  }
+
+template <int LD, int MAXM, bool USER>
+int launch_cd_warp(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
+  if (count <= 0) return EALS_OK;
+  using Sm = eals::CdWarpSmem<LD, MAXM>;
+  constexpr int kWarps = 4;
+  const size_t smem = (size_t)Sm::kBytesPerWarp * kWarps;
+  auto kern = eals::cd_warp_kernel<LD, MAXM, USER>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(count + kWarps - 1) / kWarps, kWarps * 32, smem, m->stream>>>(a, order, first, count);
+  return check_launch(m);
+}
+
+template <int LD, bool USER>
+int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
+  if (only_row >= 0) {  // single-row API: a one-entry order list in scratch
+    const int64_t n = s.h_ptr[only_row + 1] - s.h_ptr[only_row];
+    if (n == 0) return EALS_OK;
+    OK(ensure_partials(m, 16));
+    int32_t* one = reinterpret_cast<int32_t*>(m->partials);
+    CU(cudaMemcpyAsync(one, &only_row, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+    if (n <= 32) return launch_cd_warp<LD, 1, USER>(m, a, one, 0, 1);
+    if (n <= 64) return launch_cd_warp<LD, 2, USER>(m, a, one, 0, 1);
+    if (n <= 128) return launch_cd_warp<LD, 4, USER>(m, a, one, 0, 1);
+    eals::cd_cta_kernel<LD, USER><<<1, eals::kCtaThreads, 0, m->stream>>>(a, one, 0, s.long_ptr, s.pred);
+    return check_launch(m);
+  }
+  OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
+  OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+  OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+  const int nlong = s.first[5] - s.first[4];
+  if (nlong > 0) {
+    eals::cd_cta_kernel<LD, USER><<<nlong, eals::kCtaThreads, 0, m->stream>>>(a, s.order, s.first[4], s.long_ptr, s.pred);
+    OK(check_launch(m));
+  }
+  return EALS_OK;
+}
+
+int sweep(eals_model* m, bool user, int only_row) {
+  if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised (eals_init_factors / eals_set_factors)");
+  Side& s = user ? m->users : m->items;
+  CdSide a;
+  a.ptr = s.ptr; a.idx = s.idx; a.val = s.val;
+  a.X = user ? m->U : m->V;
+  a.Y = user ? m->V : m->U;
+  a.S = user ? m->SV : m->SU;
+  a.Wi = m->Wi;
+  a.row_base = s.row_base;
+  a.K = m->K;
+  a.reg = m->p.reg;
+  if (user) { DISPATCH_LD(m->LD, OK((launch_cd<LD, true>(m, s, a, only_row)))); }
+  else      { DISPATCH_LD(m->LD, OK((launch_cd<LD, false>(m, s, a, only_row)))); }
+  return sync_if_debug(m);
+}
+
+template <int LD>
+int launch_gram(eals_model* m, const double* X, const double* w, int r0, int r1, double* S) {
+  using C = eals::GramCfg<LD>;
+  int nslabs = std::max(1, std::min(2 * m->sm_count, (r1 - r0 + 127) / 128));
+  OK(ensure_partials(m, (size_t)C::NPAIR * nslabs * C::TB * C::TB));
+  dim3 grid(nslabs, C::NPAIR);
+  eals::gram_partial_kernel<LD><<<grid, eals::kGramThreads, 0, m->stream>>>(X, w, r0, r1, m->partials);
+  OK(check_launch(m));
+  const int total = C::NPAIR * C::TB * C::TB;
+  eals::gram_reduce_kernel<LD><<<(total + 255) / 256, 256, 0, m->stream>>>(m->partials, nslabs, m->K, S);
+  return check_launch(m);
+}
+
+int gram(eals_model* m, bool user, bool full) {
+  const double* X = user ? m->U : m->V;
+  const double* w = user ? nullptr : m->Wi;
+  const int r0 = full ? 0 : (user ? m->ub : m->ib);
+  const int r1 = full ? (user ? m->M : m->N) : (user ? m->ue : m->ie);
+  double* S = user ? m->SU : m->SV;
+  DISPATCH_LD(m->LD, OK(launch_gram<LD>(m, X, w, r0, r1, S)));
+  return sync_if_debug(m);
+}
+
+// Scatter dense [n][K] (host or device) into the padded [n][LD] device layout and back.
+__global__ void pad_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t n, int K, int LD) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * LD) return;
+  const size_t r = t / LD;
+  const int c = (int)(t % LD);
+  dst[t] = c < K ? src[r * K + c] : 0.0;
+}
+__global__ void unpad_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t n, int K, int LD) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * K) return;
+  const size_t r = t / K;
+  const int c = (int)(t % K);
+  dst[t] = src[r * LD + c];
+}
+
+int upload_dense(eals_model* m, double* dst, const double* src, size_t n, int space) {
+  const int K = m->K, LD = m->LD;
+  if (n == 0) return EALS_OK;
+  if (K == LD) return copy_in(dst, src, n * K, space, m->stream);
+  const double* dsrc = src;
+  double* tmp = nullptr;
+  if (space != EALS_DEVICE) {
+    OK(dev_alloc(&tmp, n * K));
+    CU(cudaMemcpyAsync(tmp, src, n * K * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    dsrc = tmp;
+  }
+  const size_t total = n * LD;
+  pad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(dsrc, dst, n, K, LD);
+  OK(check_launch(m));
+  if (tmp) { CU(cudaStreamSynchronize(m->stream)); cudaFree(tmp); }
+  return EALS_OK;
+}
+
+int download_dense(eals_model* m, double* dst, const double* src, size_t n, int space) {
+  const int K = m->K, LD = m->LD;
+  if (n == 0) return EALS_OK;
+  const cudaMemcpyKind kind = space == EALS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (K == LD) {
+    CU(cudaMemcpyAsync(dst, src, n * K * sizeof(double), kind, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return EALS_OK;
+  }
+  double* ddst = dst;
+  double* tmp = nullptr;
+  if (space != EALS_DEVICE) {
+    OK(dev_alloc(&tmp, n * K));
+    ddst = tmp;
+  }
+  const size_t total = n * K;
+  unpad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(src, ddst, n, K, LD);
+  OK(check_launch(m));
+  if (tmp) CU(cudaMemcpyAsync(dst, tmp, total * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  cudaFree(tmp);
+  return EALS_OK;
+}
+
+template <int LD>
+int launch_loss_rows(eals_model* m, const eals::LossSide& a, Side& s, int* n_partials) {
+  const int short_first = s.first[1], short_count = s.first[4] - s.first[1];
+  const int long_first = s.first[4], long_count = s.first[5] - s.first[4];
+  const int g_short = short_count ? std::min((short_count + 7) / 8, 8 * m->sm_count) : 0;
+  const int g_long = long_count ? std::min(long_count, 8 * m->sm_count) : 0;
+  OK(ensure_partials(m, (size_t)std::max(1, g_short + g_long)));
+  if (g_short) {
+    eals::loss_rows_kernel<LD, 32><<<g_short, eals::kLossThreads, 0, m->stream>>>(a, s.order, short_first, short_count, m->partials);
+    OK(check_launch(m));
+  }
+  if (g_long) {
+    eals::loss_rows_kernel<LD, 256><<<g_long, eals::kLossThreads, 0, m->stream>>>(a, s.order, long_first, long_count, m->partials + g_short);
+    OK(check_launch(m));
+  }
+  *n_partials = g_short + g_long;
+  return EALS_OK;
+}
+
+int loss_terms(eals_model* m, double terms[4]) {
+  if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised");
+  tic(m, T_LOSS);
+  eals::LossSide a;
+  Side& s = m->users;
+  a.ptr = s.ptr; a.idx = s.idx; a.val = s.val;
+  a.X = m->U; a.Y = m->V; a.Wi = m->Wi; a.row_base = s.row_base;
+  int np = 0;
+  DISPATCH_LD(m->LD, OK(launch_loss_rows<LD>(m, a, s, &np)));
+  eals::sum_partials_kernel<<<1, 256, 0, m->stream>>>(m->partials, np, m->terms + 0, 0);
+  OK(check_launch(m));
+  const int g = 4 * m->sm_count;
+  OK(ensure_partials(m, (size_t)g));
+  eals::sumsq_kernel<<<g, 256, 0, m->stream>>>(m->U, (size_t)m->ub * m->LD, (size_t)m->ue * m->LD, m->partials);
+  OK(check_launch(m));
+  eals::sum_partials_kernel<<<1, 256, 0, m->stream>>>(m->partials, g, m->terms + 1, 0);
+  OK(check_launch(m));
+  eals::sumsq_kernel<<<g, 256, 0, m->stream>>>(m->V, (size_t)m->ib * m->LD, (size_t)m->ie * m->LD, m->partials);
+  OK(check_launch(m));
+  eals::sum_partials_kernel<<<1, 256, 0, m->stream>>>(m->partials, g, m->terms + 2, 0);
+  OK(check_launch(m));
+  eals::frob_inner_kernel<<<1, 256, 0, m->stream>>>(m->SU, m->SV, m->K, m->LD, m->terms + 3);
+  OK(check_launch(m));
+  toc(m, T_LOSS);
+  CU(cudaMemcpyAsync(terms, m->terms, 4 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return EALS_OK;
+}
+
+// ---- evaluation --------------------------------------------------------------------------------
+
+double metric_ndcg(int pos) { return std::log(2) / std::log(pos + 2); }  // MF_fastALS.cpp:604-611
+
+// Rank position of gt in the reference's list (MF_fastALS.cpp:641-656) or -1.  `nz` holds the
+// (item, (int)score) pairs with a non-zero truncated score, ascending by item; every other item
+// has key 0.  The real std::partial_sort_copy runs on a sequence from which only elements that
+// cannot pass its `comp(element, heap_top)` test have been dropped, so the result is the one the
+// reference gets on the full item list.
+int reference_rank(const std::vector<std::pair<int, int>>& nz, int n_items, int topk, int gt) {
+  auto comp = [](const std::pair<int, int>& l, const std::pair<int, int>& r) { return l.second > r.second; };
+  std::vector<std::pair<int, int>> seq;
+  const int head = std::min(topk, n_items);
+  size_t q = 0;
+  bool any_negative = false;
+  for (int i = 0; i < head; i++) {
+    int key = 0;
+    if (q < nz.size() && nz[q].first == i) key = nz[q++].second;
+    any_negative |= key < 0;
+    seq.emplace_back(i, key);
+  }
+  if (any_negative) {
+    // a zero key can displace a negative heap top: keep the whole item list
+    for (int i = head; i < n_items; i++) {
+      int key = 0;
+      if (q < nz.size() && nz[q].first == i) key = nz[q++].second;
+      seq.emplace_back(i, key);
+    }
+  } else {
+    // heap top stays >= 0: only positive keys can ever pass comp(e, top)
+    for (; q < nz.size(); q++)
+      if (nz[q].second > 0) seq.push_back(nz[q]);
+  }
+  std::vector<std::pair<int, int>> top((size_t)topk, std::make_pair(0, 0));  // value-initialised (:642)
+  std::partial_sort_copy(seq.begin(), seq.end(), top.begin(), top.end(), comp);
+  for (int t = 0; t < topk; t++)
+    if (top[t].first == gt) return t;
+  return -1;
+}
+
+int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int32_t* gt_slot_h, int topk,
+                   int mode, double sums[3], double* hr, double* ndcg, double* prec, int32_t* count_larger) {
+  const int n = (int)users_h.size();
+  sums[0] = sums[1] = sums[2] = 0;
+  if (n == 0) return EALS_OK;
+  const int K = m->K, LD = m->LD, N = m->N;
+  int32_t *d_users = nullptr, *d_count = nullptr, *gt_dev = nullptr;
+  double* d_gts = nullptr;
+  OK(dev_alloc(&d_users, (size_t)n));
+  OK(dev_alloc(&gt_dev, (size_t)n));
+  CU(cudaMemcpyAsync(gt_dev, gt_slot_h, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
+  OK(dev_alloc(&d_count, (size_t)n));
+  OK(dev_alloc(&d_gts, (size_t)n));
+  CU(cudaMemcpyAsync(d_users, users_h.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemsetAsync(d_count, 0, sizeof(int32_t) * n, m->stream));
+  eals::eval_gt_score_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->U, m->V, gt_dev, d_users, 0, n, K, LD, d_gts);
+  OK(check_launch(m));
+  const int item_tiles = (N + eals::kEvalTile - 1) / eals::kEvalTile;
+  {
+    const long long tiles = (long long)((n + eals::kEvalTile - 1) / eals::kEvalTile) * item_tiles;
+    if (tiles > 0x7fffffffLL) return fail(EALS_ERR_UNSUPPORTED, "evaluate: too many tiles");
+    eals::eval_tile_kernel<0><<<(unsigned)tiles, eals::kEvalThreads, 0, m->stream>>>(
+        m->U, m->V, d_users, 0, n, N, K, LD, d_gts, d_count, nullptr, nullptr, 0);
+    OK(check_launch(m));
+  }
+  std::vector<int32_t> cnt((size_t)n);
+  CU(cudaMemcpyAsync(cnt.data(), d_count, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+
+  std::vector<int> pos((size_t)n, -1);
+  if (mode == EALS_EVAL_EXACT) {
+    for (int s = 0; s < n; s++)
+      if (cnt[s] < topk) pos[s] = cnt[s];
+  } else {
+    // survivors of the early-out (countLarger > topK -> zeros, MF_fastALS.cpp:633-634)
+    std::vector<int32_t> surv_users, surv_slot;
+    for (int s = 0; s < n; s++)
+      if (cnt[s] <= topk) { surv_users.push_back(users_h[s]); surv_slot.push_back(s); }
+    const int ns = (int)surv_users.size();
+    if (ns > 0) {
+      int32_t* d_su = nullptr;
+      unsigned long long* d_nt = nullptr;
+      eals::EvalTriple* d_tr = nullptr;
+      OK(dev_alloc(&d_su, (size_t)ns));
+      OK(dev_alloc(&d_nt, 1));
+      CU(cudaMemcpyAsync(d_su, surv_users.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, m->stream));
+      unsigned long long cap = 1ull << 20, got = 0;
+      const long long tiles = (long long)((ns + eals::kEvalTile - 1) / eals::kEvalTile) * item_tiles;
+      for (int attempt = 0; attempt < 2; attempt++) {
+        cudaFree(d_tr);
+        OK(dev_alloc(&d_tr, (size_t)cap));
+        CU(cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), m->stream));
+        eals::eval_tile_kernel<1><<<(unsigned)tiles, eals::kEvalThreads, 0, m->stream>>>(
+            m->U, m->V, d_su, 0, ns, N, K, LD, nullptr, nullptr, d_tr, d_nt, cap);
+        OK(check_launch(m));
+        CU(cudaMemcpyAsync(&got, d_nt, sizeof(got), cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        if (got <= cap) break;
+        cap = got;  // exact size known now: second pass cannot overflow
+      }
+      std::vector<eals::EvalTriple> tr((size_t)got);
+      if (got) CU(cudaMemcpy(tr.data(), d_tr, sizeof(eals::EvalTriple) * got, cudaMemcpyDeviceToHost));
+      cudaFree(d_su); cudaFree(d_nt); cudaFree(d_tr);
+      std::sort(tr.begin(), tr.end(), [](const eals::EvalTriple& a, const eals::EvalTriple& b) {
+        return a.slot != b.slot ? a.slot < b.slot : a.item < b.item;
+      });
+      size_t q = 0;
+      std::vector<std::pair<int, int>> nz;
+      for (int t = 0; t < ns; t++) {
+        nz.clear();
+        while (q < tr.size() && tr[q].slot == t) { nz.emplace_back(tr[q].item, tr[q].key); q++; }
+        pos[surv_slot[t]] = reference_rank(nz, N, topk, gt_slot_h[surv_slot[t]]);
+      }
+    }
+  }
+  for (int s = 0; s < n; s++) {
+    double r0 = 0, r1 = 0, r2 = 0;
+    if (pos[s] >= 0) { r0 = 1; r1 = metric_ndcg(pos[s]); r2 = 1.0 / (pos[s] + 1); }
+    if (hr) hr[s] = r0;
+    if (ndcg) ndcg[s] = r1;
+    if (prec) prec[s] = r2;
+    if (count_larger) count_larger[s] = std::min(cnt[s], topk + 1);
+    sums[0] += r0; sums[1] += r1; sums[2] += r2;
+  }
+  cudaFree(d_users); cudaFree(d_count); cudaFree(d_gts); cudaFree(gt_dev);
+  return EALS_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int eals_abi_version(void) { return EALS_ABI_VERSION; }
+const char* eals_last_error(void) { return g_err; }
+
+void eals_default_params(eals_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->struct_bytes = (int32_t)sizeof(eals_params);
+  p->factors = 64;      // main.cpp:133-144
+  p->topk = 10;
+  p->w0 = 10;
+  p->alpha = 0.75;
+  p->reg = 0.01;
+  p->init_mean = 0;
+  p->init_stdev = 0.01;
+  p->input_space = EALS_HOST;
+}
+
+int eals_destroy(eals_model* m) {
+  if (!m) return EALS_OK;
+  cudaSetDevice(m->p.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  free_side(m->users);
+  free_side(m->items);
+  cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
+  cudaFree(m->terms); cudaFree(m->partials);
+  for (int t = 0; t < T_COUNT; t++)
+    for (int k = 0; k < 2; k++)
+      if (m->ev[t][k]) cudaEventDestroy(m->ev[t][k]);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+  return EALS_OK;
+}
+
+int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t* col_idx,
+                const double* row_val, const int64_t* col_ptr, const int32_t* row_idx,
+                const double* col_val, eals_model** out) {
+  if (!out) return fail(EALS_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!params || params->struct_bytes != (int32_t)sizeof(eals_params))
+    return fail(EALS_ERR_ARG, "params null or struct_bytes mismatch");
+  if (!row_ptr || !col_ptr || (!col_idx && !row_idx)) return fail(EALS_ERR_ARG, "matrix arrays are null");
+  if (!col_idx || !row_idx) return fail(EALS_ERR_ARG, "both CSR and CSC index arrays are required");
+  if ((row_val == nullptr) != (col_val == nullptr)) return fail(EALS_ERR_ARG, "row_val and col_val must both be given or both be null");
+  if (params->n_users <= 0 || params->n_items <= 0) return fail(EALS_ERR_ARG, "empty matrix");
+  if (params->factors < 1 || params->factors > 256) return fail(EALS_ERR_UNSUPPORTED, "factors must be in 1..256");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(EALS_ERR_CUDA, "no CUDA device: libeals_b200 has no CPU fallback");
+  if (params->device < 0 || params->device >= ndev) return fail(EALS_ERR_ARG, "device %d out of range", params->device);
+
+  eals_model* m = new (std::nothrow) eals_model();
+  if (!m) return fail(EALS_ERR_ALLOC, "host allocation failed");
+  std::memset(m->ev, 0, sizeof(m->ev));
+  std::memset(m->timed, 0, sizeof(m->timed));
+  m->p = *params;
+  m->K = params->factors;
+  m->LD = eals::leading_dim_for(m->K);
+  m->M = params->n_users;
+  m->N = params->n_items;
+  m->ub = params->user_begin; m->ue = params->user_end;
+  m->ib = params->item_begin; m->ie = params->item_end;
+  if (m->ub == 0 && m->ue == 0) m->ue = m->M;
+  if (m->ib == 0 && m->ie == 0) m->ie = m->N;
+  auto bail = [&](int code) { eals_destroy(m); return code; };
+  if (m->ub < 0 || m->ue > m->M || m->ub > m->ue || m->ib < 0 || m->ie > m->N || m->ib > m->ie)
+    return bail(fail(EALS_ERR_ARG, "owned ranges out of bounds"));
+
+#define TRY(call) do { int r__ = (call); if (r__ != EALS_OK) return bail(r__); } while (0)
+#define TRYCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(EALS_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e__))); } while (0)
+  TRYCU(cudaSetDevice(params->device));
+  TRYCU(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  m->stream = m->own_stream;
+  TRYCU(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, params->device));
+  for (int t = 0; t < T_COUNT; t++)
+    for (int k = 0; k < 2; k++) TRYCU(cudaEventCreate(&m->ev[t][k]));
+  TRY(dev_alloc(&m->U, (size_t)m->M * m->LD));
+  TRY(dev_alloc(&m->V, (size_t)m->N * m->LD));
+  TRY(dev_alloc(&m->SU, (size_t)m->LD * m->LD));
+  TRY(dev_alloc(&m->SV, (size_t)m->LD * m->LD));
+  TRY(dev_alloc(&m->Wi, (size_t)m->N));
+  TRY(dev_alloc(&m->terms, 4));
+  TRYCU(cudaMemsetAsync(m->U, 0, sizeof(double) * (size_t)m->M * m->LD, m->stream));
+  TRYCU(cudaMemsetAsync(m->V, 0, sizeof(double) * (size_t)m->N * m->LD, m->stream));
+  TRYCU(cudaMemsetAsync(m->SU, 0, sizeof(double) * (size_t)m->LD * m->LD, m->stream));
+  TRYCU(cudaMemsetAsync(m->SV, 0, sizeof(double) * (size_t)m->LD * m->LD, m->stream));
+  TRYCU(cudaMemsetAsync(m->terms, 0, sizeof(double) * 4, m->stream));
+  TRY(build_side(m, m->users, m->ub, m->ue, m->N, params->input_space, row_ptr, col_idx, row_val));
+  TRY(build_side(m, m->items, m->ib, m->ie, m->M, params->input_space, col_ptr, row_idx, col_val));
+  TRY(compute_item_weights(m, params->input_space, col_ptr));
+  TRYCU(cudaStreamSynchronize(m->stream));
+#undef TRY
+#undef TRYCU
+  *out = m;
+  return EALS_OK;
+}
+
+int eals_set_train(eals_model* m, int32_t input_space, const int64_t* row_ptr, const int32_t* col_idx,
+                   const double* row_val, const int64_t* col_ptr, const int32_t* row_idx,
+                   const double* col_val) {
+  if (!m || !row_ptr || !col_idx || !col_ptr || !row_idx) return fail(EALS_ERR_ARG, "null argument");
+  if ((row_val == nullptr) != (col_val == nullptr)) return fail(EALS_ERR_ARG, "row_val and col_val must both be given or both be null");
+  CU(cudaSetDevice(m->p.device));
+  OK(build_side(m, m->users, m->ub, m->ue, m->N, input_space, row_ptr, col_idx, row_val));
+  OK(build_side(m, m->items, m->ib, m->ie, m->M, input_space, col_ptr, row_idx, col_val));
+  return EALS_OK;
+}
+
+int eals_refresh_S(eals_model* m) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  OK(gram(m, true, true));
+  OK(gram(m, false, true));
+  return EALS_OK;
+}
+
+int eals_init_factors(eals_model* m) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  // DenseMat::init (DenseMat.cpp:54-62): a fresh default-seeded engine per matrix, so U and V are
+  // prefixes of ONE stream; generated once with the very std:: classes the reference uses.
+  const size_t rows = (size_t)std::max(m->M, m->N);
+  std::vector<double> stream;
+  try {
+    stream.resize(rows * m->K);
+  } catch (const std::bad_alloc&) {
+    return fail(EALS_ERR_ALLOC, "host allocation of the init stream failed");
+  }
+  std::default_random_engine generator;
+  std::normal_distribution<double> distribution(m->p.init_mean, m->p.init_stdev);
+  for (size_t t = 0; t < stream.size(); t++) stream[t] = distribution(generator);
+  OK(upload_dense(m, m->U, stream.data(), (size_t)m->M, EALS_HOST));
+  OK(upload_dense(m, m->V, stream.data(), (size_t)m->N, EALS_HOST));
+  CU(cudaStreamSynchronize(m->stream));
+  m->factors_set = true;
+  return eals_refresh_S(m);
+}
+
+int eals_set_factors(eals_model* m, int32_t space, const double* U, const double* V) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  if (U) OK(upload_dense(m, m->U, U, (size_t)m->M, space));
+  if (V) OK(upload_dense(m, m->V, V, (size_t)m->N, space));
+  CU(cudaStreamSynchronize(m->stream));
+  m->factors_set = true;
+  return eals_refresh_S(m);
+}
+
+int eals_get_factors(eals_model* m, int32_t space, double* U, double* V) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  if (U) OK(download_dense(m, U, m->U, (size_t)m->M, space));
+  if (V) OK(download_dense(m, V, m->V, (size_t)m->N, space));
+  return EALS_OK;
+}
+
+int eals_set_item_weights(eals_model* m, int32_t space, const double* Wi) {
+  if (!m || !Wi) return fail(EALS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->p.device));
+  OK(copy_in(m->Wi, Wi, (size_t)m->N, space, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  if (m->factors_set) OK(gram(m, false, true));
+  return EALS_OK;
+}
+
+int eals_get_item_weights(eals_model* m, int32_t space, double* Wi) {
+  if (!m || !Wi) return fail(EALS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaMemcpyAsync(Wi, m->Wi, sizeof(double) * m->N,
+                     space == EALS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return EALS_OK;
+}
+
+int eals_get_S(eals_model* m, int32_t space, double* SU, double* SV) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  if (SU) OK(download_dense(m, SU, m->SU, (size_t)m->K, space));
+  if (SV) OK(download_dense(m, SV, m->SV, (size_t)m->K, space));
+  return EALS_OK;
+}
+
+int eals_sweep_users(eals_model* m) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  tic(m, T_USER_SWEEP);
+  OK(sweep(m, true, -1));
+  toc(m, T_USER_SWEEP);
+  return EALS_OK;
+}
+int eals_sweep_items(eals_model* m) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  tic(m, T_ITEM_SWEEP);
+  OK(sweep(m, false, -1));
+  toc(m, T_ITEM_SWEEP);
+  return EALS_OK;
+}
+int eals_gram_users(eals_model* m) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  tic(m, T_USER_GRAM);
+  OK(gram(m, true, false));
+  toc(m, T_USER_GRAM);
+  return EALS_OK;
+}
+int eals_gram_items(eals_model* m) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  tic(m, T_ITEM_GRAM);
+  OK(gram(m, false, false));
+  toc(m, T_ITEM_GRAM);
+  return EALS_OK;
+}
+int eals_update_user(eals_model* m) {
+  OK(eals_sweep_users(m));
+  return eals_gram_users(m);
+}
+int eals_update_item(eals_model* m) {
+  OK(eals_sweep_items(m));
+  return eals_gram_items(m);
+}
+
+int eals_update_user_row(eals_model* m, int32_t u) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  if (u < m->ub || u >= m->ue) return fail(EALS_ERR_ARG, "user %d not owned by this model", u);
+  CU(cudaSetDevice(m->p.device));
+  return sweep(m, true, u - m->ub);
+}
+int eals_update_item_row(eals_model* m, int32_t i) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  if (i < m->ib || i >= m->ie) return fail(EALS_ERR_ARG, "item %d not owned by this model", i);
+  CU(cudaSetDevice(m->p.device));
+  return sweep(m, false, i - m->ib);
+}
+
+static int patch_S(eals_model* m, double* S, double scale, const double* old_row, const double* new_row) {
+  if (!old_row || !new_row) return fail(EALS_ERR_ARG, "null row");
+  CU(cudaSetDevice(m->p.device));
+  OK(ensure_partials(m, (size_t)2 * m->K + 16));
+  CU(cudaMemcpyAsync(m->partials, old_row, sizeof(double) * m->K, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->partials + m->K, new_row, sizeof(double) * m->K, cudaMemcpyHostToDevice, m->stream));
+  const int total = m->K * m->K;
+  eals::gram_patch_kernel<<<(total + 255) / 256, 256, 0, m->stream>>>(S, m->partials, m->partials + m->K, scale, m->K, m->LD);
+  OK(check_launch(m));
+  CU(cudaStreamSynchronize(m->stream));  // the host rows may be reused by the caller
+  return EALS_OK;
+}
+int eals_patch_SU(eals_model* m, const double* old_row, const double* new_row) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  return patch_S(m, m->SU, 1.0, old_row, new_row);
+}
+int eals_patch_SV(eals_model* m, int32_t i, const double* old_row, const double* new_row) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  if (i < 0 || i >= m->N) return fail(EALS_ERR_ARG, "item out of range");
+  double wi = 0;
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaMemcpyAsync(&wi, m->Wi + i, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return patch_S(m, m->SV, wi, old_row, new_row);
+}
+
+int eals_loss_terms(eals_model* m, double terms[4]) {
+  if (!m || !terms) return fail(EALS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->p.device));
+  return loss_terms(m, terms);
+}
+int eals_loss(eals_model* m, double* loss) {
+  if (!m || !loss) return fail(EALS_ERR_ARG, "null argument");
+  double t[4];
+  OK(eals_loss_terms(m, t));
+  *loss = m->p.reg * (t[1] + t[2]) + t[0] + t[3];
+  return EALS_OK;
+}
+
+int eals_predict(eals_model* m, int32_t u, int32_t i, double* score) {
+  if (!m || !score) return fail(EALS_ERR_ARG, "null argument");
+  if (u < 0 || u >= m->M || i < 0 || i >= m->N) return fail(EALS_ERR_ARG, "index out of range");
+  CU(cudaSetDevice(m->p.device));
+  OK(ensure_partials(m, 16));
+  int32_t* d_gt = reinterpret_cast<int32_t*>(m->partials + 8);
+  CU(cudaMemcpyAsync(d_gt, &i, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
+  eals::eval_gt_score_kernel<<<1, 32, 0, m->stream>>>(m->U, m->V, d_gt, nullptr, u, 1, m->K, m->LD, m->partials);
+  OK(check_launch(m));
+  CU(cudaMemcpyAsync(score, m->partials, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return EALS_OK;
+}
+
+int eals_evaluate(eals_model* m, const int32_t* gt_items, int32_t topk, int32_t mode, double sums[3],
+                  double* hr, double* ndcg, double* prec, int32_t* count_larger) {
+  if (!m || !gt_items || !sums) return fail(EALS_ERR_ARG, "null argument");
+  if (topk < 1) return fail(EALS_ERR_ARG, "topk must be >= 1");
+  if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised");
+  CU(cudaSetDevice(m->p.device));
+  for (int u = m->ub; u < m->ue; u++)
+    if (gt_items[u] < 0 || gt_items[u] >= m->N) return fail(EALS_ERR_ARG, "gt item of user %d out of range", u);
+  std::vector<int32_t> users((size_t)(m->ue - m->ub));
+  for (int u = m->ub; u < m->ue; u++) users[u - m->ub] = u;
+  tic(m, T_EVAL);
+  const int r = evaluate_slots(m, users, gt_items + m->ub, topk, mode, sums, hr, ndcg, prec, count_larger);
+  toc(m, T_EVAL);
+  return r;
+}
+
+int eals_evaluate_user(eals_model* m, int32_t u, int32_t gt_item, int32_t topk, int32_t mode, double out[3]) {
+  if (!m || !out) return fail(EALS_ERR_ARG, "null argument");
+  if (u < 0 || u >= m->M || gt_item < 0 || gt_item >= m->N || topk < 1) return fail(EALS_ERR_ARG, "argument out of range");
+  if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised");
+  CU(cudaSetDevice(m->p.device));
+  std::vector<int32_t> users(1, u);
+  return evaluate_slots(m, users, &gt_item, topk, mode, out, nullptr, nullptr, nullptr, nullptr);
+}
+
+int eals_leading_dim(const eals_model* m) { return m ? m->LD : 0; }
+
+int eals_device_buffer(eals_model* m, int32_t which, void** dev_ptr, int64_t* bytes) {
+  if (!m || !dev_ptr) return fail(EALS_ERR_ARG, "null argument");
+  void* p = nullptr;
+  int64_t b = 0;
+  switch (which) {
+    case EALS_BUF_U: p = m->U; b = (int64_t)m->M * m->LD * 8; break;
+    case EALS_BUF_V: p = m->V; b = (int64_t)m->N * m->LD * 8; break;
+    case EALS_BUF_SU: p = m->SU; b = (int64_t)m->K * m->LD * 8; break;
+    case EALS_BUF_SV: p = m->SV; b = (int64_t)m->K * m->LD * 8; break;
+    case EALS_BUF_WI: p = m->Wi; b = (int64_t)m->N * 8; break;
+    case EALS_BUF_LOSS_TERMS: p = m->terms; b = 32; break;
+    default: return fail(EALS_ERR_ARG, "unknown buffer %d", which);
+  }
+  *dev_ptr = p;
+  if (bytes) *bytes = b;
+  return EALS_OK;
+}
+
+int eals_stream(eals_model* m, void** cuda_stream) {
+  if (!m || !cuda_stream) return fail(EALS_ERR_ARG, "null argument");
+  *cuda_stream = (void*)m->stream;
+  return EALS_OK;
+}
+
+int eals_set_stream(eals_model* m, void* cuda_stream) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaStreamSynchronize(m->stream));
+  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  return EALS_OK;
+}
+
+int eals_sync(eals_model* m) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaStreamSynchronize(m->stream));
+  CU(cudaGetLastError());
+  return EALS_OK;
+}
+
+int64_t eals_nnz(const eals_model* m) { return m ? m->users.nnz : 0; }
+int64_t eals_kernel_launches(const eals_model* m) { return m ? m->launches : 0; }
+
+int eals_timings(eals_model* m, double ms[6]) {
+  if (!m || !ms) return fail(EALS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaStreamSynchronize(m->stream));
+  for (int t = 0; t < T_COUNT; t++) {
+    ms[t] = 0;
+    if (m->timed[t]) {
+      float f = 0;
+      CU(cudaEventElapsedTime(&f, m->ev[t][0], m->ev[t][1]));
+      ms[t] = f;
+    }
+  }
+  return EALS_OK;
+}
+
+}  // extern "C"

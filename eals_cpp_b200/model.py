@@ -1,0 +1,416 @@
+"""Host-side mirror of the reference's ``MF_fastALS`` class (MF_fastALS.h:15-80) over the C ABI.
+
+This is plumbing, not the product: every number comes out of libeals_b200.so (hand-written sm_100a
+kernels).  Python is used here because the tests and bench.py are Python and because the
+multi-GPU launch model is one process per GPU under ``torch.distributed``; the C++ drop-in class
+of the same name is ``include/MF_fastALS.h``.  Names, argument order and print formats follow the
+reference:
+
+    fals = MF_fastALS(trainMatrix, testRatings, topK, threadNum, factors, maxIter, w0, alpha, reg,
+                      init_mean, init_stdev, showProgress, showLoss, userCount, itemCount)
+    fals.buildModel()                        # MF_fastALS.cpp:112-161
+    fals.loss()                              # :184-206
+    fals.evaluate()                          # evaluate_model, main.cpp:37-65
+    fals.evaluate_for_user(u, gtItem, topK)  # :620-662
+
+Multi-GPU: every rank holds full replicas of U and V and owns a contiguous,
+nnz-balanced user range and item range.  After each half-epoch the updated rows are exchanged
+(one broadcast per owner, straight into the replica — the all-gather of variable-size shards) and
+the partial K x K Grams are all-reduced.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import EalsParams, check
+
+
+# --------------------------------------------------------------------------------------------------
+# SparseMat: the train matrix in both orientations (SparseMat.h:15-42 holds rows[] and cols[]).
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class SparseMat:
+    """Dual CSR/CSC container.  Arrays are numpy (host) or torch CUDA tensors (device):
+    ``row_ptr`` int64 [M+1], ``col_idx`` int32 [nnz] ascending per row (main.cpp:198-205 order),
+    ``col_ptr`` int64 [N+1], ``row_idx`` int32 [nnz] ascending per column; ``row_val``/``col_val``
+    fp64 or None (all ratings 1, which is what the reference's loader stores)."""
+    M: int
+    N: int
+    row_ptr: object
+    col_idx: object
+    col_ptr: object
+    row_idx: object
+    row_val: object = None
+    col_val: object = None
+
+    @property
+    def on_device(self) -> bool:
+        return not isinstance(self.row_ptr, np.ndarray)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.row_ptr[-1])
+
+    @staticmethod
+    def from_csr(M, N, row_ptr, col_idx, val=None) -> "SparseMat":
+        """Build the column orientation from a host CSR (stable sort by column keeps users
+        ascending inside a column, as the reference's append order does)."""
+        row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        col_idx = np.ascontiguousarray(col_idx, np.int32)
+        rows = np.repeat(np.arange(M, dtype=np.int32), np.diff(row_ptr))
+        order = np.argsort(col_idx, kind="stable")
+        col_ptr = np.zeros(N + 1, np.int64)
+        np.cumsum(np.bincount(col_idx, minlength=N), out=col_ptr[1:])
+        row_val = col_val = None
+        if val is not None:
+            row_val = np.ascontiguousarray(val, np.float64)
+            col_val = np.ascontiguousarray(row_val[order])
+        return SparseMat(M, N, row_ptr, col_idx, col_ptr, np.ascontiguousarray(rows[order]), row_val, col_val)
+
+    @staticmethod
+    def from_csr_device(M, N, row_ptr, col_idx) -> "SparseMat":
+        """Same, for torch CUDA tensors (all-ones ratings)."""
+        from .datasets import csr_to_csc_device
+        col_ptr, row_idx, _ = csr_to_csc_device(M, N, row_ptr, col_idx)
+        return SparseMat(M, N, row_ptr.contiguous(), col_idx.contiguous(), col_ptr, row_idx)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())          # torch tensor
+
+
+def partition_by_nnz(ptr, world: int) -> list[int]:
+    """Contiguous row ranges with (nearly) equal nonzero counts: bounds[r]..bounds[r+1] is rank r's
+    range.  ``ptr`` is the host offsets array of that orientation."""
+    ptr = np.asarray(ptr)
+    n = len(ptr) - 1
+    total = int(ptr[-1])
+    bounds = [0]
+    for r in range(1, world):
+        b = int(np.searchsorted(ptr, total * r / world, side="left"))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return bounds
+
+
+def exchange_rows(full, bounds, rank: int, group=None) -> None:
+    """All-gather of variable-size shards: rows bounds[r]:bounds[r+1] of the replicated matrix
+    ``full`` (a torch tensor [n][ld], CPU for gloo or CUDA for nccl) are sent from rank r into
+    every other replica, in place."""
+    import torch.distributed as dist
+    world = len(bounds) - 1
+    for r in range(world):
+        if bounds[r + 1] > bounds[r]:
+            src = dist.get_global_rank(group, r) if group is not None else r
+            dist.broadcast(full[bounds[r]:bounds[r + 1]], src=src, group=group)
+
+
+def allreduce_sum(t, group=None) -> None:
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class MF_fastALS:
+    def __init__(self, trainMatrix: SparseMat, testRatings, topK=10, threadNum=1, factors=64,
+                 maxIter=20, w0=10.0, alpha=0.75, reg=0.01, init_mean=0.0, init_stdev=0.01,
+                 showProgress=False, showLoss=True, userCount=None, itemCount=None, *,
+                 device=None, distributed=None, init=True, debug_sync=False, out=None):
+        self.lib = _lib.load()
+        self.trainMatrix = trainMatrix
+        self.userCount = int(userCount if userCount is not None else trainMatrix.M)
+        self.itemCount = int(itemCount if itemCount is not None else trainMatrix.N)
+        if self.userCount != trainMatrix.M or self.itemCount != trainMatrix.N:
+            raise ValueError("userCount/itemCount do not match the train matrix")
+        self.topK, self.factors, self.maxIter = int(topK), int(factors), int(maxIter)
+        self.w0, self.alpha, self.reg = float(w0), float(alpha), float(reg)
+        self.init_mean, self.init_stdev = float(init_mean), float(init_stdev)
+        self.showprogress, self.showloss = bool(showProgress), bool(showLoss)
+        del threadNum                                   # dead in the reference too (MF_fastALS.cpp:30)
+        self.out = out or sys.stdout
+        self.testItems = None if testRatings is None else self._test_items(testRatings)
+
+        # distributed context: one process per GPU
+        self.rank, self.world, self.group = 0, 1, None
+        if distributed is None:
+            try:
+                import torch.distributed as dist
+                distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            except ImportError:
+                distributed = False
+        if distributed:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if device is None:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = int(device)
+
+        sm = trainMatrix
+        if self.world > 1:
+            rp = sm.row_ptr if isinstance(sm.row_ptr, np.ndarray) else sm.row_ptr.cpu().numpy()
+            cp = sm.col_ptr if isinstance(sm.col_ptr, np.ndarray) else sm.col_ptr.cpu().numpy()
+            self.user_bounds = partition_by_nnz(rp, self.world)
+            self.item_bounds = partition_by_nnz(cp, self.world)
+        else:
+            self.user_bounds, self.item_bounds = [0, sm.M], [0, sm.N]
+
+        p = EalsParams()
+        self.lib.eals_default_params(C.byref(p))
+        p.n_users, p.n_items, p.factors, p.topk = sm.M, sm.N, self.factors, self.topK
+        p.w0, p.alpha, p.reg = self.w0, self.alpha, self.reg
+        p.init_mean, p.init_stdev = self.init_mean, self.init_stdev
+        p.device = self.device
+        p.input_space = _lib.EALS_DEVICE if sm.on_device else _lib.EALS_HOST
+        p.user_begin, p.user_end = self.user_bounds[self.rank], self.user_bounds[self.rank + 1]
+        p.item_begin, p.item_end = self.item_bounds[self.rank], self.item_bounds[self.rank + 1]
+        p.flags = _lib.FLAG_SYNC_EACH_CALL if debug_sync else 0
+        if self.world > 1 and (p.user_end == p.user_begin or p.item_end == p.item_begin):
+            raise ValueError("more ranks than rows: a rank would own an empty range")
+        self._params = p
+        h = C.c_void_p()
+        check(self.lib.eals_create(C.byref(p), _ptr(sm.row_ptr), _ptr(sm.col_idx), _ptr(sm.row_val),
+                                   _ptr(sm.col_ptr), _ptr(sm.row_idx), _ptr(sm.col_val), C.byref(h)))
+        self.h = h
+        self.ld = self.lib.eals_leading_dim(self.h)
+        if self.world > 1:
+            # order the library's kernels with torch's NCCL calls: share torch's current stream
+            import torch
+            check(self.lib.eals_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        if init:
+            check(self.lib.eals_init_factors(self.h))     # MF_fastALS.cpp:85-90
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _test_items(self, testRatings):
+        a = np.asarray(testRatings)
+        if a.ndim == 2:                                  # rows of (userId, itemId, ...) like Rating.h
+            items = np.empty(self.userCount, np.int32)
+            items[a[:, 0].astype(np.int64)] = a[:, 1].astype(np.int32)
+            return items
+        return np.ascontiguousarray(a, np.int32)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.eals_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_tensor(self, which):
+        """torch view (no copy) of one of the model's device buffers, padded leading dimension."""
+        import torch
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        check(self.lib.eals_device_buffer(self.h, which, C.byref(ptr), C.byref(nbytes)))
+        if which in (_lib.BUF_WI, _lib.BUF_LOSS_TERMS):
+            shape = (nbytes.value // 8,)
+        else:
+            shape = (nbytes.value // 8 // self.ld, self.ld)
+        return torch.as_tensor(_DevArray(ptr.value, shape), device=f"cuda:{self.device}")
+
+    def sync(self):
+        check(self.lib.eals_sync(self.h))
+
+    # ---- public members of the reference (MF_fastALS.h:31-46) as host copies ------------------------
+    def _get_factors(self, want_u, want_v):
+        U = np.empty((self.userCount, self.factors)) if want_u else None
+        V = np.empty((self.itemCount, self.factors)) if want_v else None
+        check(self.lib.eals_get_factors(self.h, _lib.EALS_HOST, _ptr(U), _ptr(V)))
+        return U, V
+
+    @property
+    def U(self):
+        return self._get_factors(True, False)[0]
+
+    @property
+    def V(self):
+        return self._get_factors(False, True)[1]
+
+    def _get_S(self, su, sv):
+        SU = np.empty((self.factors, self.factors)) if su else None
+        SV = np.empty((self.factors, self.factors)) if sv else None
+        check(self.lib.eals_get_S(self.h, _lib.EALS_HOST, _ptr(SU), _ptr(SV)))
+        return SU, SV
+
+    @property
+    def SU(self):
+        return self._get_S(True, False)[0]
+
+    @property
+    def SV(self):
+        return self._get_S(False, True)[1]
+
+    @property
+    def Wi(self):
+        w = np.empty(self.itemCount)
+        check(self.lib.eals_get_item_weights(self.h, _lib.EALS_HOST, _ptr(w)))
+        return w
+
+    @Wi.setter
+    def Wi(self, w):
+        w = np.ascontiguousarray(w, np.float64)
+        check(self.lib.eals_set_item_weights(self.h, _lib.EALS_HOST, _ptr(w)))
+
+    # ---- setters (MF_fastALS.cpp:94-110) -------------------------------------------------------------
+    def setUV(self, U, V):
+        if isinstance(U, np.ndarray) or U is None and isinstance(V, np.ndarray):
+            U = None if U is None else np.ascontiguousarray(U, np.float64)
+            V = None if V is None else np.ascontiguousarray(V, np.float64)
+            space = _lib.EALS_HOST
+        else:
+            space = _lib.EALS_DEVICE
+        check(self.lib.eals_set_factors(self.h, space, _ptr(U), _ptr(V)))
+
+    def setTrain(self, trainMatrix: SparseMat):
+        sm = trainMatrix
+        space = _lib.EALS_DEVICE if sm.on_device else _lib.EALS_HOST
+        check(self.lib.eals_set_train(self.h, space, _ptr(sm.row_ptr), _ptr(sm.col_idx), _ptr(sm.row_val),
+                                      _ptr(sm.col_ptr), _ptr(sm.row_idx), _ptr(sm.col_val)))
+        self.trainMatrix = sm
+
+    # ---- half-epochs ---------------------------------------------------------------------------------
+    def update_user(self):
+        """User sweep + SU refresh (MF_fastALS.cpp:127-132)."""
+        check(self.lib.eals_sweep_users(self.h))
+        if self.world > 1:
+            exchange_rows(self.device_tensor(_lib.BUF_U), self.user_bounds, self.rank, self.group)
+        check(self.lib.eals_gram_users(self.h))
+        if self.world > 1:
+            allreduce_sum(self.device_tensor(_lib.BUF_SU), self.group)
+
+    def update_item(self):
+        """Item sweep + SV refresh (MF_fastALS.cpp:146-152)."""
+        check(self.lib.eals_sweep_items(self.h))
+        if self.world > 1:
+            exchange_rows(self.device_tensor(_lib.BUF_V), self.item_bounds, self.rank, self.group)
+        check(self.lib.eals_gram_items(self.h))
+        if self.world > 1:
+            allreduce_sum(self.device_tensor(_lib.BUF_SV), self.group)
+
+    def update_user_thread(self, u):
+        check(self.lib.eals_update_user_row(self.h, int(u)))
+
+    def update_item_thread(self, i):
+        check(self.lib.eals_update_item_row(self.h, int(i)))
+
+    def update_user_SU(self, oldVector, uget):
+        o, n = np.ascontiguousarray(oldVector, np.float64), np.ascontiguousarray(uget, np.float64)
+        check(self.lib.eals_patch_SU(self.h, _ptr(o), _ptr(n)))
+
+    def update_item_SV(self, i, oldVector, vget):
+        o, n = np.ascontiguousarray(oldVector, np.float64), np.ascontiguousarray(vget, np.float64)
+        check(self.lib.eals_patch_SV(self.h, int(i), _ptr(o), _ptr(n)))
+
+    def runOneIteration(self):
+        """One correct epoch (the reference's version leaves the S caches stale: :163-173)."""
+        self.update_user()
+        self.update_item()
+
+    # ---- loss / predict --------------------------------------------------------------------------------
+    def loss(self) -> float:
+        terms = np.zeros(4)
+        check(self.lib.eals_loss_terms(self.h, _ptr(terms)))
+        if self.world > 1:
+            import torch
+            t = torch.from_numpy(terms[:3].copy()).to(f"cuda:{self.device}")
+            allreduce_sum(t, self.group)
+            terms[:3] = t.cpu().numpy()
+        return float(self.reg * (terms[1] + terms[2]) + terms[0] + terms[3])
+
+    def predict(self, u, i) -> float:
+        s = C.c_double()
+        check(self.lib.eals_predict(self.h, int(u), int(i), C.byref(s)))
+        return s.value
+
+    def showLoss(self, it, t, loss_pre):
+        t0 = time.perf_counter()
+        cur = self.loss()
+        sym = "-" if loss_pre >= cur else "+"
+        if self.rank == 0:
+            print(f"Iter={it} {t:g} {sym} loss:{cur:g} {time.perf_counter() - t0:g}", file=self.out)
+        return cur
+
+    def buildModel(self):
+        """maxIter x (user half-epoch, item half-epoch, optional loss) — MF_fastALS.cpp:112-161,
+        with the reference's three stdout lines per iteration."""
+        loss_pre = float("inf")
+        self.losses = []
+        for it in range(self.maxIter):
+            t0 = time.perf_counter()
+            self.update_user()
+            self.sync()
+            t_user = time.perf_counter() - t0
+            if self.rank == 0:
+                print(f"Time of user_update: {t_user:g}", file=self.out)
+            t0 = time.perf_counter()
+            self.update_item()
+            self.sync()
+            t_item = time.perf_counter() - t0
+            if self.rank == 0:
+                print(f"Time of item_update: {t_item:g}", file=self.out)
+            if self.showloss:
+                loss_pre = self.showLoss(it, t_user + t_item, loss_pre)
+                self.losses.append(loss_pre)
+
+    # ---- evaluation --------------------------------------------------------------------------------------
+    def evaluate_for_user(self, u, gtItem, topK=None, exact=False):
+        out = np.zeros(3)
+        check(self.lib.eals_evaluate_user(self.h, int(u), int(gtItem), int(topK or self.topK),
+                                          _lib.EVAL_EXACT if exact else _lib.EVAL_REFERENCE, _ptr(out)))
+        return [float(x) for x in out]
+
+    def evaluate(self, testRatings=None, topK=None, exact=False, per_user=False):
+        """evaluate_model (main.cpp:37-65): mean HR, NDCG and reciprocal rank over ALL users.
+        ``exact=False`` reproduces the reference's int-truncating ranking bug for bug."""
+        items = self.testItems if testRatings is None else self._test_items(testRatings)
+        topK = int(topK or self.topK)
+        n_own = self.user_bounds[self.rank + 1] - self.user_bounds[self.rank]
+        sums = np.zeros(3)
+        hr = ndcg = prec = cnt = None
+        if per_user:
+            hr, ndcg, prec = np.zeros(n_own), np.zeros(n_own), np.zeros(n_own)
+            cnt = np.zeros(n_own, np.int32)
+        check(self.lib.eals_evaluate(self.h, _ptr(items), topK,
+                                     _lib.EVAL_EXACT if exact else _lib.EVAL_REFERENCE, _ptr(sums),
+                                     _ptr(hr), _ptr(ndcg), _ptr(prec), _ptr(cnt)))
+        if self.world > 1:
+            import torch
+            t = torch.from_numpy(sums.copy()).to(f"cuda:{self.device}")
+            allreduce_sum(t, self.group)
+            sums = t.cpu().numpy()
+        res = sums / self.userCount
+        if per_user:
+            return res, hr, ndcg, prec, cnt
+        return res
+
+    # ---- instrumentation -----------------------------------------------------------------------------------
+    def timings(self):
+        ms = np.zeros(6)
+        check(self.lib.eals_timings(self.h, _ptr(ms)))
+        return dict(zip(("user_sweep", "user_gram", "item_sweep", "item_gram", "loss", "evaluate"), ms.tolist()))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.eals_kernel_launches(self.h))
+
+    def owned_nnz(self) -> int:
+        return int(self.lib.eals_nnz(self.h))

@@ -1,0 +1,193 @@
+/* eals_b200.h — C ABI of libeals_b200.so: the device side of the eALS trainer for NVIDIA B200
+ * (sm_100a).  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * What it replaces.  The reference (QihanW/eals_cpp) has no FFI layer: its boundary is the C++
+ * class MF_fastALS (MF_fastALS.h:15-80) driven from main.cpp:227-231,49.  Our host class of the
+ * same name (include/MF_fastALS.h) keeps that surface and forwards every hot call to the entry
+ * points below; each one names the reference member it stands in for.  A maintainer of the
+ * reference binds the same symbols.
+ *
+ * Conventions.
+ *  - The popularity weights and the factor initialisation run on the HOST inside the library with
+ *    the same libm / libstdc++ calls the reference makes (pow; default_random_engine +
+ *    normal_distribution), so they are bit-identical to the reference by construction.
+ *  - Every function returns 0 (EALS_OK) or a negative eals_status; eals_last_error() gives the
+ *    message for the calling thread.  Nothing throws across the ABI.
+ *  - One eals_model lives on ONE GPU and is driven by ONE host thread (the reference's methods are
+ *    not reentrant either: MF_fastALS.h:40-45).  Multi-GPU = one process (and one model) per GPU;
+ *    each model owns a contiguous user range and item range (eals_params.user_begin ...) and holds
+ *    full replicas of U and V.  The exchange between half-epochs (all-gather of the updated factor
+ *    rows, all-reduce of the partial K x K Gram) is performed by the host on the device buffers
+ *    exposed through eals_device_buffer().
+ *  - Index arrays are int32 (row/column ids) and int64 (offsets); values are IEEE fp64.
+ *    CSR rows ascend by item id, CSC columns ascend by user id, no duplicates: the order
+ *    main.cpp:198-205 fills SparseMat.rows/cols in.
+ *  - Sweeps are enqueued on the model's stream and return without waiting; calls that hand a value
+ *    back to the host (loss, evaluate, get_*) synchronise.  eals_sync() waits explicitly.
+ *  - There is no CPU fallback: without a CUDA device every call fails with EALS_ERR_CUDA.
+ */
+#ifndef EALS_B200_H
+#define EALS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EALS_ABI_VERSION 1
+
+typedef enum eals_status {
+  EALS_OK = 0,
+  EALS_ERR_ARG = -1,         /* null pointer, bad range, unsorted/duplicate indices ...           */
+  EALS_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...)               */
+  EALS_ERR_ALLOC = -3,       /* device or host allocation failed                                  */
+  EALS_ERR_STATE = -4,       /* call not valid in the model's current state                       */
+  EALS_ERR_UNSUPPORTED = -5  /* e.g. factors > 256                                                */
+} eals_status;
+
+typedef enum eals_space { EALS_HOST = 0, EALS_DEVICE = 1 } eals_space;
+
+typedef enum eals_buffer {
+  EALS_BUF_U = 0,     /* [n_users][ld]  fp64, ld = eals_leading_dim(), padding columns are zero   */
+  EALS_BUF_V = 1,     /* [n_items][ld]                                                            */
+  EALS_BUF_SU = 2,    /* [factors][ld]  S cache U^T U (this rank's partial until reduced)         */
+  EALS_BUF_SV = 3,    /* [factors][ld]  S cache V^T diag(Wi) V                                    */
+  EALS_BUF_WI = 4,    /* [n_items]                                                                */
+  EALS_BUF_LOSS_TERMS = 5 /* [4] fp64, see eals_loss_terms                                        */
+} eals_buffer;
+
+typedef enum eals_eval_mode {
+  EALS_EVAL_REFERENCE = 0, /* bug-for-bug: int-truncating comparator + libstdc++ heap order
+                              (MF_fastALS.cpp:643-651)                                            */
+  EALS_EVAL_EXACT = 1      /* rank position = number of strictly larger scores                    */
+} eals_eval_mode;
+
+/* Constructor arguments of MF_fastALS (MF_fastALS.h:52-55) that reach the device side.
+ * threadNum, showProgress and showLoss stay in the host class (threadNum is dead in the reference
+ * too: MF_fastALS.cpp:30). */
+typedef struct eals_params {
+  int32_t struct_bytes;   /* sizeof(eals_params), for ABI evolution                               */
+  int32_t n_users;        /* userCount                                                            */
+  int32_t n_items;        /* itemCount                                                            */
+  int32_t factors;        /* K, 1..256                                                            */
+  int32_t topk;           /* default topK for evaluate                                            */
+  double w0;              /* weight of missing data                                               */
+  double alpha;           /* popularity exponent                                                  */
+  double reg;             /* L2 regularisation                                                    */
+  double init_mean;       /* N(mean, stdev) factor initialisation                                 */
+  double init_stdev;
+  int32_t device;         /* CUDA ordinal                                                         */
+  int32_t input_space;    /* eals_space of the matrix pointers given to eals_create               */
+  int32_t user_begin;     /* rows [user_begin, user_end) are updated by this model                */
+  int32_t user_end;       /*   (0, n_users for a single GPU; 0,0 means "all")                     */
+  int32_t item_begin;
+  int32_t item_end;
+  int32_t flags;          /* EALS_FLAG_*                                                          */
+  int32_t reserved;
+} eals_params;
+
+#define EALS_FLAG_SYNC_EACH_CALL 1 /* debugging: synchronise + check after every enqueue          */
+
+typedef struct eals_model eals_model;
+
+int eals_abi_version(void);
+const char* eals_last_error(void);
+void eals_default_params(eals_params* p); /* run.sh defaults of main.cpp:133-144                  */
+
+/* MF_fastALS::MF_fastALS (MF_fastALS.cpp:29-92) minus the factor initialisation: copies the train
+ * matrix to the device (the caller may free its arrays on return), derives the popularity weights
+ * Wi (MF_fastALS.cpp:55-72) and allocates U, V, SU, SV (zero).  row_val / col_val may
+ * be NULL: all ratings 1 (what the reference's loader stores, main.cpp:184-185,202); otherwise the
+ * value is both the rating and its confidence weight (W is a copy of the ratings,
+ * MF_fastALS.cpp:75-82).  All six arrays describe the FULL matrix even when the model owns a
+ * sub-range. */
+int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t* col_idx,
+                const double* row_val, const int64_t* col_ptr, const int32_t* row_idx,
+                const double* col_val, eals_model** out);
+int eals_destroy(eals_model* m);
+
+/* MF_fastALS::setTrain (MF_fastALS.cpp:94-104): replace the train matrix (same shape). Wi is kept,
+ * as in the reference. */
+int eals_set_train(eals_model* m, int32_t input_space, const int64_t* row_ptr,
+                   const int32_t* col_idx, const double* row_val, const int64_t* col_ptr,
+                   const int32_t* row_idx, const double* col_val);
+
+/* U.init / V.init / initS of the constructor (MF_fastALS.cpp:85-90, DenseMat.cpp:54-62): the
+ * default-seeded libstdc++ minstd_rand0 + polar normal stream, the SAME stream for U and V, then
+ * both S caches. */
+int eals_init_factors(eals_model* m);
+
+/* MF_fastALS::setUV (MF_fastALS.cpp:106-110), working: dense row-major [n][factors] fp64 in the
+ * given space; either pointer may be NULL to keep that side.  Refreshes the S caches (initS). */
+int eals_set_factors(eals_model* m, int32_t space, const double* U, const double* V);
+int eals_get_factors(eals_model* m, int32_t space, double* U, double* V);
+
+/* Public member Wi (MF_fastALS.h:46). set refreshes SV. */
+int eals_set_item_weights(eals_model* m, int32_t space, const double* Wi);
+int eals_get_item_weights(eals_model* m, int32_t space, double* Wi);
+
+/* initS (MF_fastALS.cpp:583-595) and read-back of SU, SV as dense [factors][factors]. */
+int eals_refresh_S(eals_model* m);
+int eals_get_S(eals_model* m, int32_t space, double* SU, double* SV);
+
+/* One half-epoch each, as buildModel runs them (MF_fastALS.cpp:127-132 and :146-152):
+ * update_user_thread for every owned user (:243-322) then the SU refresh (:324-335; recomputed as
+ * a Gram over the owned rows instead of patched row by row); same for items (:338-407, :409-422).
+ * Enqueue-only.  With more than one rank the host must all-gather the updated rows of U (V) and
+ * all-reduce SU (SV) before the next half-epoch. */
+int eals_update_user(eals_model* m);
+int eals_update_item(eals_model* m);
+
+/* The two stages of the above, separately (for hosts that overlap the exchange). */
+int eals_sweep_users(eals_model* m);
+int eals_sweep_items(eals_model* m);
+int eals_gram_users(eals_model* m);
+int eals_gram_items(eals_model* m);
+
+/* Single-row forms MF_fastALS::update_user_thread(u) / update_item_thread(i) — no S refresh — and
+ * the rank-1 S patches update_user_SU / update_item_SV (MF_fastALS.cpp:324-335, 409-422) with
+ * host vectors of `factors` doubles. */
+int eals_update_user_row(eals_model* m, int32_t u);
+int eals_update_item_row(eals_model* m, int32_t i);
+int eals_patch_SU(eals_model* m, const double* old_row, const double* new_row);
+int eals_patch_SV(eals_model* m, int32_t i, const double* old_row, const double* new_row);
+
+/* MF_fastALS::loss (MF_fastALS.cpp:184-206).  terms[0] = sum over OWNED users of the per-nonzero
+ * part, terms[1] = |U owned rows|^2, terms[2] = |V owned rows|^2, terms[3] = sum_u u^T SV u taken
+ * as <SU, SV>_F (needs SU, SV current and complete).  loss = terms[0] + reg*(terms[1]+terms[2]) +
+ * terms[3]; eals_loss forms that for a single-rank model. */
+int eals_loss_terms(eals_model* m, double terms[4]);
+int eals_loss(eals_model* m, double* loss);
+
+/* MF_fastALS::predict (MF_fastALS.cpp:208-221). */
+int eals_predict(eals_model* m, int32_t u, int32_t i, double* score);
+
+/* evaluate_model + evaluate_for_user (main.cpp:37-65, MF_fastALS.cpp:620-662) over the OWNED
+ * users.  gt_items: host array indexed by global user id (n_users entries).  sums[3] = sum of
+ * hit-ratio, NDCG and reciprocal rank ("prec") over the owned users — divide by n_users after
+ * summing across ranks.  Optional per-user host outputs have (user_end-user_begin) entries;
+ * count_larger is the number of items scoring strictly above the held-out one, capped at topk+1. */
+int eals_evaluate(eals_model* m, const int32_t* gt_items, int32_t topk, int32_t mode,
+                  double sums[3], double* hr, double* ndcg, double* prec, int32_t* count_larger);
+int eals_evaluate_user(eals_model* m, int32_t u, int32_t gt_item, int32_t topk, int32_t mode,
+                       double out[3]);
+
+/* Plumbing for the host layer. */
+int eals_leading_dim(const eals_model* m);                 /* ld of U/V/SU/SV rows, in doubles   */
+int eals_device_buffer(eals_model* m, int32_t which, void** dev_ptr, int64_t* bytes);
+int eals_stream(eals_model* m, void** cuda_stream);        /* cudaStream_t the model enqueues on  */
+/* Make the model enqueue on a caller-owned stream (e.g. the one the host's NCCL calls are ordered
+ * against); NULL restores the model's own stream.  Synchronises the old stream first. */
+int eals_set_stream(eals_model* m, void* cuda_stream);
+int eals_sync(eals_model* m);
+int64_t eals_nnz(const eals_model* m);                     /* nonzeros of the owned user rows     */
+int64_t eals_kernel_launches(const eals_model* m);         /* kernels launched so far             */
+/* Device milliseconds of the most recent call of each kind: [0] user sweep, [1] user Gram,
+ * [2] item sweep, [3] item Gram, [4] loss, [5] evaluate.  Synchronises. */
+int eals_timings(eals_model* m, double ms[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EALS_B200_H */

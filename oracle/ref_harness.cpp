@@ -53,8 +53,8 @@ SparseMat build_sparse(int M, int N, const int64_t* row_ptr, const int32_t* col_
 }
 
 struct CoutSilencer {
+  std::ostringstream sink;   // declared (hence constructed) before `old`, whose initialiser uses it
   std::streambuf* old;
-  std::ostringstream sink;
   CoutSilencer() : old(std::cout.rdbuf(sink.rdbuf())) {}
   ~CoutSilencer() { std::cout.rdbuf(old); }
 };

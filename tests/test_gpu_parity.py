@@ -1,0 +1,158 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (fp64 everywhere; only the summation ORDER over a row's nonzeros and over rows differs
+from the reference's sequential loops):
+  * factors after a half-epoch:   |dU| <= 1e-11 absolute (values are O(0.01..1))
+  * per-epoch loss:               <= 1e-10 relative (north star allows 1e-6)
+  * S caches:                     <= 1e-12 relative to the largest entry
+  * evaluation: count_larger and the HR/NDCG/reciprocal-rank tuples identical per user — scores are
+    computed with the reference's exact operation order (sequential k, no FMA), so they are
+    bit-identical, and the ranking replay uses the same libstdc++ partial_sort_copy.
+"""
+import numpy as np
+import pytest
+
+from conftest import random_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(M, N, row_ptr, col_idx, K, val=None, **kw):
+    from eals_cpp_b200.model import MF_fastALS, SparseMat
+    from oracle.bindings import PortModel
+    sm = SparseMat.from_csr(M, N, row_ptr, col_idx, val)
+    fals = MF_fastALS(sm, None, factors=K, showLoss=False, debug_sync=True, **kw)
+    port = PortModel(M, N, row_ptr, col_idx, val, factors=K, **kw)
+    return fals, port
+
+
+@pytest.mark.parametrize("K", [8, 16, 64, 128, 20])
+def test_init_and_S_match_oracle(K):
+    row_ptr, col_idx = random_csr(300, 200, 12, seed=K)
+    fals, port = _models(300, 200, row_ptr, col_idx, K)
+    assert np.array_equal(fals.U, port.U)            # same libstdc++ stream
+    assert np.array_equal(fals.V, port.V)
+    assert np.allclose(fals.Wi, port.Wi, rtol=1e-15, atol=0)
+    for got, want in ((fals.SU, port.SU), (fals.SV, port.SV)):
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("K", [8, 64, 128])
+@pytest.mark.parametrize("shape", [(400, 300, 14), (120, 900, 150), (900, 60, 10)])
+def test_half_epochs_and_loss_match_oracle(K, shape):
+    M, N, dens = shape
+    row_ptr, col_idx = random_csr(M, N, dens, seed=M + K, empty_frac=0.05)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for it in range(3):
+        fals.update_user(); port.update_user()
+        assert np.abs(fals.U - port.U).max() < 1e-11, f"U after user sweep {it}"
+        fals.update_item(); port.update_item()
+        assert np.abs(fals.V - port.V).max() < 1e-11, f"V after item sweep {it}"
+        lg, lc = fals.loss(), port.loss()
+        assert abs(lg - lc) <= 1e-10 * abs(lc), (it, lg, lc)
+    assert np.abs(fals.SU - port.SU).max() <= 1e-11 * np.abs(port.SU).max()
+    assert np.abs(fals.SV - port.SV).max() <= 1e-11 * np.abs(port.SV).max()
+
+
+def test_weighted_ratings_match_oracle():
+    """Non-unit ratings: W is a copy of the rating values (MF_fastALS.cpp:75-82)."""
+    M, N, K = 200, 150, 16
+    row_ptr, col_idx = random_csr(M, N, 10, seed=5)
+    val = np.random.default_rng(1).uniform(0.5, 3.0, size=len(col_idx))
+    fals, port = _models(M, N, row_ptr, col_idx, K, val=val)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+    assert np.abs(fals.U - port.U).max() < 1e-11
+    assert np.abs(fals.V - port.V).max() < 1e-11
+    lg, lc = fals.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc)
+
+
+def test_long_rows_use_cta_path():
+    """Rows far longer than a warp tile (CTA kernel) and a dense column."""
+    M, N, K = 64, 2000, 64
+    rng = np.random.default_rng(3)
+    row_ptr, cols = [0], []
+    for u in range(M):
+        n = 1500 if u % 7 == 0 else int(rng.integers(1, 300))
+        cols.append(np.sort(rng.choice(N, size=n, replace=False)).astype(np.int32))
+        row_ptr.append(row_ptr[-1] + n)
+    row_ptr, col_idx = np.asarray(row_ptr, np.int64), np.concatenate(cols)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+    assert np.abs(fals.U - port.U).max() < 1e-10
+    assert np.abs(fals.V - port.V).max() < 1e-10
+    lg, lc = fals.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc)
+
+
+def test_single_row_api_and_patches():
+    M, N, K = 150, 120, 16
+    row_ptr, col_idx = random_csr(M, N, 9, seed=9)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    u = 17
+    old = fals.U[u].copy()
+    fals.update_user_thread(u)
+    port.update_user(u, u + 1)                   # oracle: same row, SU patched for that row
+    new = fals.U[u]
+    assert np.abs(new - port.U[u]).max() < 1e-12
+    fals.update_user_SU(old, new)
+    assert np.abs(fals.SU - port.SU).max() <= 1e-12 * np.abs(port.SU).max()
+    i = 5
+    oldv = fals.V[i].copy()
+    fals.update_item_thread(i)
+    port.update_item(i, i + 1)
+    assert np.abs(fals.V[i] - port.V[i]).max() < 1e-12
+    fals.update_item_SV(i, oldv, fals.V[i])
+    assert np.abs(fals.SV - port.SV).max() <= 1e-12 * np.abs(port.SV).max()
+    assert fals.predict(3, 4) == port_predict(port, 3, 4)   # sequential-k, no FMA: bit-identical
+
+
+def port_predict(port, u, i):
+    acc = 0.0
+    for k in range(port.K):
+        acc += port.U[u, k] * port.V[i, k]
+    return acc
+
+
+@pytest.mark.parametrize("scale", [1.0, 40.0])
+def test_evaluate_matches_oracle_bug_for_bug(scale):
+    """scale=40 inflates the factors so that truncated scores are non-zero (and some negative):
+    exercises the heap replay beyond the all-zero-keys case."""
+    M, N, K, topK = 500, 333, 16, 10
+    row_ptr, col_idx = random_csr(M, N, 12, seed=21)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+    if scale != 1.0:
+        rng = np.random.default_rng(2)
+        U = port.U * scale + rng.normal(0, 0.5, port.U.shape)
+        V = port.V * scale + rng.normal(0, 0.5, port.V.shape)
+        port.U[:], port.V[:] = U, V
+        fals.setUV(U, V)
+    gt = np.random.default_rng(4).integers(0, N, size=M).astype(np.int32)
+    gt[:40] = np.arange(40) % 12                  # some gt items inside the first topK ids
+    for compat in (True, False):
+        want_mean, whr, wndcg, wprec, wcnt = port.evaluate(gt, topK, compat=compat)
+        got_mean, hr, ndcg, prec, cnt = fals.evaluate(gt, topK, exact=not compat, per_user=True)
+        assert np.array_equal(cnt, wcnt)
+        assert np.array_equal(hr, whr) and np.array_equal(ndcg, wndcg) and np.array_equal(prec, wprec)
+        assert np.allclose(got_mean, want_mean, rtol=0, atol=1e-15)
+    _, whr, wndcg, wprec, _ = port.evaluate(gt, topK, compat=True)
+    for u in (0, 7, 39, 123):
+        assert fals.evaluate_for_user(u, int(gt[u]), topK) == [whr[u], wndcg[u], wprec[u]]
+
+
+def test_errors_are_reported_not_swallowed():
+    from eals_cpp_b200._lib import EalsError
+    from eals_cpp_b200.model import MF_fastALS, SparseMat
+    row_ptr = np.array([0, 2, 3], np.int64)
+    col_idx = np.array([1, 0, 2], np.int32)         # row 0 not ascending
+    sm = SparseMat.from_csr(2, 3, row_ptr, col_idx)
+    sm.col_idx = col_idx                             # keep the bad order
+    with pytest.raises(EalsError):
+        MF_fastALS(sm, None, factors=8)
