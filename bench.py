@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py — eALS epoch throughput on B200 (BASELINE.json metric: nnz*K updates/s, epoch time).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1|c4s|small]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path on the host cores
+
+A step = one eALS epoch (user half-epoch + item half-epoch, each incl. the S-cache Gram and, with
+N > 1, the exchange of the updated factor rows and the all-reduce of the partial Grams) — what the
+reference prints as the 2nd field of its `Iter=` line (MF_fastALS.cpp:125-158).  loss()/evaluate()
+are outside the timed region, as in the reference.
+
+value  = 2*nnz*K / epoch seconds, inputs resident in HBM, device-timed (CUDA events, max over ranks)
+e2e    = same metric through the public API with HOST (pinned) train-matrix buffers: every step
+         uploads the CSR+CSC arrays (setTrain), runs the epoch and reads the loss back.
+Workload: the north-star target configuration (BASELINE.json configs[3], "c4": 10M x 2M, 500M
+interactions, K=128) — it fits one B200 (about 25 GB), so it is also the N=1 workload; N > 1 shards
+the SAME matrix (strong scaling).  Synthetic power-law data (no dataset ships with the reference).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "eals_nnzK_updates_per_s"
+UNIT = "nnz*K updates/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def cd_bytes_per_epoch(M, N, K, nnz_user_side, nnz_item_side, rows_u, rows_i):
+    """Algorithmic bytes of the two CD sweeps, all-ones ratings:
+    every nonzero gathers the other side's K-vector once per sweep (K*8 B) and its index (4 B);
+    every updated row is read and written once (2*K*8 B); offsets 8 B per row; Wi 8 B per item
+    read on the user side (per nonzero it is an L2-resident gather, counted once per item) and once
+    per row on the item side."""
+    s = 8
+    return ((nnz_user_side + nnz_item_side) * (K * s + 4)
+            + 2 * (rows_u + rows_i) * K * s
+            + (rows_u + rows_i + 2) * 8
+            + 2 * N * s)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: NVML sampler thread (nvidia-smi's numbers without forking)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.1):
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.period = period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:            # pragma: no cover
+            self.nv = None
+            self.err = repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        if self.nv:
+            self.t.join(timeout=2)
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------
+def build_workload(name, device):
+    """Synthetic matrix of the named shape, generated on the GPU (torch = plumbing: RNG/sort)."""
+    import torch
+    from eals_cpp_b200 import datasets
+    from eals_cpp_b200.model import SparseMat
+    spec = dict(datasets.WORKLOADS[name])
+    t0 = time.perf_counter()
+    with torch.cuda.device(device):
+        row_ptr, col_idx, test_items = datasets.powerlaw_csr_device(device=f"cuda:{device}", **spec)
+        sm = SparseMat.from_csr_device(spec["M"], spec["N"], row_ptr, col_idx)
+        torch.cuda.synchronize()
+    log(f"[bench] workload {name}: M={spec['M']} N={spec['N']} nnz={sm.nnz} K={spec['K']} "
+        f"generated in {time.perf_counter() - t0:.1f}s")
+    return spec, sm, test_items
+
+
+def random_factors(M, N, K, device, seed=1234):
+    """N(0, 0.01) factors on the device — the reference's init distribution (main.cpp:141-142); the
+    libstdc++-exact sequential stream is used by the parity tests, not at 1.5e9 values."""
+    import torch
+    g = torch.Generator(device=f"cuda:{device}")
+    g.manual_seed(seed)
+    U = torch.randn(M, K, generator=g, device=f"cuda:{device}", dtype=torch.float64) * 0.01
+    V = torch.randn(N, K, generator=g, device=f"cuda:{device}", dtype=torch.float64) * 0.01
+    return U, V
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU side (test infrastructure used as the reported baseline / the reference arm)
+# --------------------------------------------------------------------------------------------------
+def cpu_port_sample(sm, K, reg, w0, alpha, target_nnz, threads, seed=7):
+    """Time the oracle port (oracle/eals_oracle.c: the reference's update_user_thread /
+    update_item_thread arithmetic on flat arrays) on a bounded sample of this workload: the first
+    users and the first items whose rows hold ~target_nnz nonzeros each, with the factor rows they
+    gather compacted into dense host arrays.  Rows are independent inside a half-epoch, so `threads`
+    host threads each take a contiguous sub-range (ctypes releases the GIL)."""
+    import torch
+    from oracle.bindings import Port
+    port = Port()
+    rng = np.random.default_rng(seed)
+
+    def side(ptr_t, idx_t, n_other):
+        ptr = ptr_t.cpu().numpy() if hasattr(ptr_t, "cpu") else np.asarray(ptr_t)
+        rows = int(np.searchsorted(ptr, target_nnz, side="left"))
+        rows = max(1, min(rows, len(ptr) - 1))
+        nnz = int(ptr[rows])
+        idx = idx_t[:nnz]
+        if hasattr(idx, "cpu"):
+            uniq, inv = torch.unique(idx.long(), return_inverse=True)
+            uniq, inv = uniq.cpu().numpy(), inv.cpu().numpy().astype(np.int32)
+        else:
+            uniq, inv = np.unique(np.asarray(idx), return_inverse=True)
+            inv = inv.astype(np.int32)
+        return np.ascontiguousarray(ptr[:rows + 1]), np.ascontiguousarray(inv), uniq, rows, nnz
+
+    def fill(n):      # N(0, 0.01) block tiled: timing does not depend on the values
+        base = rng.normal(0, 0.01, (min(n, 4096), K))
+        return np.ascontiguousarray(np.tile(base, ((n + len(base) - 1) // len(base), 1))[:n])
+
+    out = {}
+    # user side: sampled users gather item vectors
+    rp, ci, items, Mu, nnz_u = side(sm.row_ptr, sm.col_idx, sm.N)
+    # item side: sampled items gather user vectors
+    cp, ri, users, Ni, nnz_i = side(sm.col_ptr, sm.row_idx, sm.M)
+
+    def run(fn, ptr, idx, X, Y, SX, SY, Wi, nrows):
+        bounds = np.linspace(0, nrows, threads + 1).astype(int)
+        # balance by nnz rather than rows
+        tot = ptr[nrows]
+        bounds = [int(np.searchsorted(ptr, tot * t / threads)) for t in range(threads)] + [nrows]
+        ths = [threading.Thread(target=fn, args=(ptr, idx, None, X, Y, SX, SY, Wi, reg, bounds[t], bounds[t + 1], False))
+               for t in range(threads) if bounds[t + 1] > bounds[t]]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0
+
+    # user sweep: X = U[Mu], Y = V compact
+    U = fill(Mu)
+    Vc = fill(len(items))
+    Wi = np.full(len(items), w0 / max(sm.N, 1))
+    SV = Vc.T @ (Vc * Wi[:, None]) * (sm.N / max(len(items), 1))
+    SU = np.eye(K)
+    t_user = run(lambda p, i, v, X, Y, SX, SY, W, r, b, e, ps: port.update_user_sweep(p, i, v, X, Y, SX, SY, W, r, b, e, ps),
+                 rp, ci, U, Vc, SU, SV, Wi, Mu)
+    # item sweep: X = V[Ni], Y = U compact
+    V = fill(Ni)
+    Uc = fill(len(users))
+    Wi2 = np.full(Ni, w0 / max(sm.N, 1))
+    SU2 = Uc.T @ Uc * (sm.M / max(len(users), 1))
+    t_item = run(lambda p, i, v, X, Y, SX, SY, W, r, b, e, ps: port.update_item_sweep(p, i, v, Y, X, SY, SX, W, r, b, e, ps),
+                 cp, ri, V, Uc, np.eye(K), SU2, Wi2, Ni)
+    nnz = sm.nnz
+    epoch_s = nnz / (nnz_u / t_user) + nnz / (nnz_i / t_item)     # extrapolated whole-epoch CPU time
+    out.update(value=2.0 * nnz * K / epoch_s, unit=UNIT, cores=threads, kind="port",
+               sample=(f"oracle port (eals_oracle.c, gcc -O2) on the first {Mu} users ({nnz_u} nnz, {t_user:.2f}s) and "
+                       f"first {Ni} items ({nnz_i} nnz, {t_item:.2f}s) of this workload, gathered factor rows "
+                       f"compacted on the host, {threads} threads over disjoint row ranges, S patch excluded; "
+                       f"extrapolated epoch {epoch_s:.1f}s"),
+               epoch_s_extrapolated=epoch_s, sample_seconds=t_user + t_item)
+    return out
+
+
+def cpu_reference_full(sm_host, K, steps, warmup):
+    """The real MF_fastALS object (oracle/_ref, -O3 build), whole epochs, 1 thread."""
+    from oracle.bindings import Reference
+    ref = Reference(sm_host.M, sm_host.N, sm_host.row_ptr, sm_host.col_idx, factors=K, fast=True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ref.update_user()
+        ref.update_item()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return float(np.mean(times))
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("EALS_BENCH_WORKLOAD", "c4"))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-nnz", type=int, default=0, help="nonzeros per side in the CPU sample (0 = auto)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+
+    from eals_cpp_b200.model import MF_fastALS, SparseMat
+    spec, sm, test_items = build_workload(args.workload, local_rank)
+    M, N, K, nnz = spec["M"], spec["N"], spec["K"], sm.nnz
+    fals = MF_fastALS(sm, None, topK=spec["topK"], factors=K, showLoss=False, init=False, device=local_rank)
+    U0, V0 = random_factors(M, N, K, local_rank)
+    fals.setUV(U0, V0)
+    del U0, V0
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def epoch():
+        fals.update_user()
+        fals.update_item()
+
+    for _ in range(args.warmup):
+        epoch()
+    barrier()
+    fals.timings_total(reset=True)
+    launches0 = fals.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            epoch()
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    launches = fals.kernel_launches() - launches0
+    phase_ms, phase_calls = fals.timings_total(reset=True)
+    value = 2.0 * nnz * K / (ms_step * 1e-3)
+
+    # roofline of the dominant kernel family: the CD sweeps (this rank's owned rows)
+    peaks, peak_src = measured_peaks()
+    ub, ue = fals.user_bounds[rank], fals.user_bounds[rank + 1]
+    ib, ie = fals.item_bounds[rank], fals.item_bounds[rank + 1]
+    nnz_u = int(sm.row_ptr[ue] - sm.row_ptr[ub])
+    nnz_i = int(sm.col_ptr[ie] - sm.col_ptr[ib])
+    alg_bytes = cd_bytes_per_epoch(M, N, K, nnz_u, nnz_i, ue - ub, ie - ib)
+    sweep_ms = (phase_ms["user_sweep"] + phase_ms["item_sweep"]) / args.steps
+    achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(args.workload, {}).get("cd_sweep_dram_bytes_per_epoch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "cd_sweep (user + item CD sweep kernels of one epoch)",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": sweep_ms, "peak_source": peak_src}
+
+    loss = fals.loss()
+
+    # ---- e2e: through the public API with HOST buffers -------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def pinned(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            return h
+        keep = [pinned(x) for x in (sm.row_ptr, sm.col_idx, sm.col_ptr, sm.row_idx)]
+        sm_host = SparseMat(M, N, *[k.numpy() for k in keep])
+        own_u = int(sm.row_ptr[ue] - sm.row_ptr[ub]); own_i = int(sm.col_ptr[ie] - sm.col_ptr[ib])
+        h2d = (own_u + own_i) * 4 + (ue - ub + 1 + ie - ib + 1) * 8      # what the library uploads per step
+        times = []
+        for it in range(1 + args.e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            fals.setTrain(sm_host)          # H2D of the CSR + CSC slices, bucketing
+            epoch()
+            _ = fals.loss()                 # D2H of the step's result
+            barrier()
+            if it > 0:
+                times.append(time.perf_counter() - t0)
+        t_e2e = float(np.mean(times))
+        if world > 1:
+            t = torch.tensor([t_e2e, float(h2d)], device=f"cuda:{local_rank}", dtype=torch.float64)
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t_e2e, h2d = float(tmax[0].item()), int(t[1].item())
+        e2e = {"value": 2.0 * nnz * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 32 * world, "s_per_step": t_e2e, "steps": args.e2e_steps,
+               "what": "setTrain(host pinned CSR+CSC) + update_user + update_item + loss() per step"}
+        del keep, sm_host
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu and world == 1:
+        try:
+            threads = os.cpu_count() or 1
+            target = args.cpu_nnz or min(nnz // 2, 4_000_000)
+            cpu = cpu_port_sample(sm, K, 0.01, 10.0, 0.75, max(target, 1000), threads)
+        except Exception as e:      # the baseline must never take the GPU number down with it
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {M} users x {N} items, {nnz} interactions, K={K}, "
+                                   f"power-law (Zipf {spec['zipf']}) synthetic, all ratings 1, w0=10 alpha=0.75 reg=0.01",
+                       "step": "one eALS epoch = update_user + update_item incl. S-cache Gram and (N>1) exchange",
+                       "parallelism": f"users/items sharded over {world} GPU(s), U/V replicated",
+                       "l2": "inputs (>= 12 GB of factors + 4 GB of indices) far exceed the 126 MB L2; no flush needed"
+                             if args.workload in ("c4", "c4s", "c3") else "working set fits L2: latency/launch-bound",
+                       "baseline_note": "BASELINE.md's only published figure (8.16e7 /s) is the reference on real yelp.rating, K=64, 1 CPU thread — a different config"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items() if phase_calls[k]},
+            "loss_after": loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(args):
+    """The reference's CPU implementation of the same path on the host cores.  For workloads the
+    real MF_fastALS object can hold (c1/c2/small) it is oracle/_ref (the reference's own TUs, -O3,
+    single-threaded as the reference is); for the large ones a bounded sample through the oracle
+    port on every host core."""
+    import __graft_entry__ as g
+    g.build()
+    from eals_cpp_b200 import datasets
+    from eals_cpp_b200.model import SparseMat
+    name = args.workload
+    spec = dict(datasets.WORKLOADS[name])
+    K = spec["K"]
+    small = spec["nnz"] <= 2_000_000
+    times = []
+    if small:
+        from oracle import bindings
+        data = datasets.powerlaw_csr(**spec)
+        sm = SparseMat.from_csr(data.M, data.N, data.row_ptr, data.col_idx)
+        nnz = sm.nnz
+        if bindings.reference_available(fast=True):
+            t = cpu_reference_full(sm, K, args.steps, min(args.warmup, 1))
+            kind, cores = "reference", 1
+            sample = f"oracle/_ref (reference TUs, g++ -O3 -march=x86-64-v3), whole epochs incl. S patches, 1 thread, mean of {args.steps}"
+            value = 2.0 * nnz * K / t
+            times = [t]
+        else:
+            r = cpu_port_sample(sm, K, 0.01, 10.0, 0.75, nnz, 1)
+            kind, cores, sample, value = "port", 1, r["sample"], r["value"]
+            times = [r["epoch_s_extrapolated"]]
+    else:
+        import torch
+        assert torch.cuda.is_available(), "the large synthetic workloads are generated on the GPU"
+        _, sm, _ = build_workload(name, 0)
+        nnz = sm.nnz
+        threads = os.cpu_count() or 1
+        target = args.cpu_nnz or min(nnz // 2, 4_000_000)
+        vals = []
+        for it in range(min(args.warmup, 1) + args.steps):
+            r = cpu_port_sample(sm, K, 0.01, 10.0, 0.75, max(target, 1000), threads, seed=7 + it)
+            if it >= min(args.warmup, 1):
+                vals.append(r["value"]); times.append(r["epoch_s_extrapolated"])
+        kind, cores, sample, value = "port", threads, r["sample"], float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {spec['M']} users x {spec['N']} items, {nnz} interactions, K={K}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

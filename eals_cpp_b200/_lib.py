@@ -70,11 +70,12 @@ SIGNATURES = {
     "eals_leading_dim": (C.c_int, [_P]),
     "eals_device_buffer": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "eals_stream": (C.c_int, [_P, C.POINTER(_P)]),
-    "eals_set_stream": (C.c_int, [_P, _P]),
+    "eals_set_stream": (C.c_int, [_P, _P, C.c_int32]),
     "eals_sync": (C.c_int, [_P]),
     "eals_nnz": (C.c_int64, [_P]),
     "eals_kernel_launches": (C.c_int64, [_P]),
     "eals_timings": (C.c_int, [_P, _P]),
+    "eals_timings_total": (C.c_int, [_P, _P, _P, C.c_int32]),
 }
 
 _lib = None

@@ -96,8 +96,11 @@ struct eals_model {
   Side users, items;
   int sm_count = 148;
   int64_t launches = 0;
-  cudaEvent_t ev[T_COUNT][2];
-  bool timed[T_COUNT];
+  double last_ms[T_COUNT] = {0};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[T_COUNT];  // not yet folded into acc_ms
+  std::vector<cudaEvent_t> pool;
+  double acc_ms[T_COUNT] = {0};
+  int64_t acc_calls[T_COUNT] = {0};
   bool factors_set = false;
 };
 
@@ -265,10 +268,40 @@ int ensure_partials(eals_model* m, size_t n) {
   return EALS_OK;
 }
 
-void tic(eals_model* m, int which) { cudaEventRecord(m->ev[which][0], m->stream); }
+cudaEvent_t take_event(eals_model* m) {
+  cudaEvent_t e = nullptr;
+  if (!m->pool.empty()) { e = m->pool.back(); m->pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+
+// Fold finished event pairs into the accumulators (caller has synchronised the stream).
+void fold_timings(eals_model* m) {
+  for (int t = 0; t < T_COUNT; t++) {
+    for (auto& pr : m->pending[t]) {
+      float f = 0;
+      if (pr.second && cudaEventElapsedTime(&f, pr.first, pr.second) == cudaSuccess) {
+        m->acc_ms[t] += f;
+        m->acc_calls[t]++;
+        m->last_ms[t] = f;
+      }
+      m->pool.push_back(pr.first);
+      if (pr.second) m->pool.push_back(pr.second);
+    }
+    m->pending[t].clear();
+  }
+}
+
+void tic(eals_model* m, int which) {
+  if (m->pending[which].size() >= 2048) { cudaStreamSynchronize(m->stream); fold_timings(m); }
+  cudaEvent_t e = take_event(m);
+  cudaEventRecord(e, m->stream);
+  m->pending[which].emplace_back(e, nullptr);
+}
 void toc(eals_model* m, int which) {
-  cudaEventRecord(m->ev[which][1], m->stream);
-  m->timed[which] = true;
+  cudaEvent_t e = take_event(m);
+  cudaEventRecord(e, m->stream);
+  m->pending[which].back().second = e;
 }
 
 // ---- dispatch on the leading dimension (16, 32, 64, 128, 256) ---------------------------------
@@ -622,9 +655,8 @@ int eals_destroy(eals_model* m) {
   free_side(m->items);
   cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
   cudaFree(m->terms); cudaFree(m->partials);
-  for (int t = 0; t < T_COUNT; t++)
-    for (int k = 0; k < 2; k++)
-      if (m->ev[t][k]) cudaEventDestroy(m->ev[t][k]);
+  fold_timings(m);
+  for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
   return EALS_OK;
@@ -649,8 +681,6 @@ int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t
 
   eals_model* m = new (std::nothrow) eals_model();
   if (!m) return fail(EALS_ERR_ALLOC, "host allocation failed");
-  std::memset(m->ev, 0, sizeof(m->ev));
-  std::memset(m->timed, 0, sizeof(m->timed));
   m->p = *params;
   m->K = params->factors;
   m->LD = eals::leading_dim_for(m->K);
@@ -670,8 +700,6 @@ int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t
   TRYCU(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
   TRYCU(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, params->device));
-  for (int t = 0; t < T_COUNT; t++)
-    for (int k = 0; k < 2; k++) TRYCU(cudaEventCreate(&m->ev[t][k]));
   TRY(dev_alloc(&m->U, (size_t)m->M * m->LD));
   TRY(dev_alloc(&m->V, (size_t)m->N * m->LD));
   TRY(dev_alloc(&m->SU, (size_t)m->LD * m->LD));
@@ -936,11 +964,12 @@ int eals_stream(eals_model* m, void** cuda_stream) {
   return EALS_OK;
 }
 
-int eals_set_stream(eals_model* m, void* cuda_stream) {
+int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own) {
   if (!m) return fail(EALS_ERR_ARG, "null model");
   CU(cudaSetDevice(m->p.device));
   CU(cudaStreamSynchronize(m->stream));
-  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  fold_timings(m);
+  m->stream = restore_own ? m->own_stream : (cudaStream_t)cuda_stream;
   return EALS_OK;
 }
 
@@ -959,13 +988,20 @@ int eals_timings(eals_model* m, double ms[6]) {
   if (!m || !ms) return fail(EALS_ERR_ARG, "null argument");
   CU(cudaSetDevice(m->p.device));
   CU(cudaStreamSynchronize(m->stream));
+  fold_timings(m);
+  for (int t = 0; t < T_COUNT; t++) ms[t] = m->last_ms[t];
+  return EALS_OK;
+}
+
+int eals_timings_total(eals_model* m, double ms[6], int64_t calls[6], int32_t reset) {
+  if (!m) return fail(EALS_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaStreamSynchronize(m->stream));
+  fold_timings(m);
   for (int t = 0; t < T_COUNT; t++) {
-    ms[t] = 0;
-    if (m->timed[t]) {
-      float f = 0;
-      CU(cudaEventElapsedTime(&f, m->ev[t][0], m->ev[t][1]));
-      ms[t] = f;
-    }
+    if (ms) ms[t] = m->acc_ms[t];
+    if (calls) calls[t] = m->acc_calls[t];
+    if (reset) { m->acc_ms[t] = 0; m->acc_calls[t] = 0; }
   }
   return EALS_OK;
 }

@@ -190,10 +190,10 @@ class MF_fastALS:
                                    _ptr(sm.col_ptr), _ptr(sm.row_idx), _ptr(sm.col_val), C.byref(h)))
         self.h = h
         self.ld = self.lib.eals_leading_dim(self.h)
-        if self.world > 1:
-            # order the library's kernels with torch's NCCL calls: share torch's current stream
-            import torch
-            check(self.lib.eals_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        # order the library's kernels with torch's (NCCL calls, CUDA events): share torch's current stream
+        import torch
+        with torch.cuda.device(self.device):
+            check(self.lib.eals_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream), 0))
         if init:
             check(self.lib.eals_init_factors(self.h))     # MF_fastALS.cpp:85-90
 
@@ -408,6 +408,14 @@ class MF_fastALS:
         ms = np.zeros(6)
         check(self.lib.eals_timings(self.h, _ptr(ms)))
         return dict(zip(("user_sweep", "user_gram", "item_sweep", "item_gram", "loss", "evaluate"), ms.tolist()))
+
+    PHASES = ("user_sweep", "user_gram", "item_sweep", "item_gram", "loss", "evaluate")
+
+    def timings_total(self, reset=False):
+        """Accumulated device ms and call counts per phase since the last reset."""
+        ms, calls = np.zeros(6), np.zeros(6, np.int64)
+        check(self.lib.eals_timings_total(self.h, _ptr(ms), _ptr(calls), int(reset)))
+        return dict(zip(self.PHASES, ms.tolist())), dict(zip(self.PHASES, calls.tolist()))
 
     def kernel_launches(self) -> int:
         return int(self.lib.eals_kernel_launches(self.h))

@@ -1,0 +1,210 @@
+// MF_fastALS.h — C++ drop-in host class over libeals_b200.so (include/eals_b200.h).
+//
+// Mirrors the public surface of the reference's class MF_fastALS (MF_fastALS.h:15-80): same
+// constructor argument list (MF_fastALS.h:52-55), same method names and meanings, same stdout lines
+// (MF_fastALS.cpp:134,155,179).  Every hot call is forwarded to the C ABI; nothing is computed on
+// the CPU here apart from flattening the caller's SparseMat into CSR/CSC arrays.
+//
+// The class is a template over the caller's container types so that it works with the reference's
+// own SparseMat / Rating (duck-typed: `n_r`, `n_c`, `rows[u].n`, `rows[u].spv_in[j]`,
+// `rows[u].spv_do[j]`, `cols[i]...`; `Rating::itemId`) as well as with the small CSR-backed
+// containers in eals_host_types.h.  A reference maintainer writes
+//
+//     #include "SparseMat.h"            // theirs
+//     #include "Rating.h"               // theirs
+//     #include "MF_fastALS.h"           // this file instead of theirs
+//     using MF_fastALS = eals_b200::MF_fastALS_T<SparseMat, Rating>;
+//
+// and main.cpp:227-231 compiles unchanged.  Differences from the reference, all
+// deliberate (SURVEY.md §9 "Drop"): the object is non-copyable (the reference double-frees when
+// copied, main.cpp:37 / MF_fastALS.cpp:664-673); inputs are copied to the device at construction,
+// so the caller's arrays need not outlive the model; errors throw std::runtime_error with the
+// library's message instead of being ignored; runOneIteration() refreshes the S caches.
+#ifndef EALS_B200_MF_FASTALS_H
+#define EALS_B200_MF_FASTALS_H
+
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "eals_b200.h"
+
+namespace eals_b200 {
+
+inline void check(int code, const char* what) {
+  if (code != EALS_OK)
+    throw std::runtime_error(std::string(what) + ": " + eals_last_error() + " (code " + std::to_string(code) + ")");
+}
+
+template <class SparseMatT, class RatingT>
+class MF_fastALS_T {
+ public:
+  // public data members of the reference that callers read (MF_fastALS.h:19-29,48-49)
+  int factors, maxIter;
+  double reg, w0, init_mean, init_stdev;
+  int itemCount, userCount, topK;
+  double alpha;
+  bool showprogress, showloss;
+  std::vector<RatingT> testRatings;
+
+  MF_fastALS_T(const SparseMatT& trainMatrix, const std::vector<RatingT>& testRatings_, int topK_,
+               int threadNum, int factors_, int maxIter_, double w0_, double alpha_, double reg_,
+               double init_mean_, double init_stdev_, bool showProgress, bool showLoss, int userCount_,
+               int itemCount_, int device = 0)
+      : factors(factors_), maxIter(maxIter_), reg(reg_), w0(w0_), init_mean(init_mean_),
+        init_stdev(init_stdev_), itemCount(itemCount_), userCount(userCount_), topK(topK_),
+        alpha(alpha_), showprogress(showProgress), showloss(showLoss), testRatings(testRatings_) {
+    (void)threadNum;  // accepted and ignored, as in the reference (MF_fastALS.cpp:30)
+    eals_params p;
+    eals_default_params(&p);
+    p.n_users = userCount; p.n_items = itemCount; p.factors = factors; p.topk = topK;
+    p.w0 = w0; p.alpha = alpha; p.reg = reg; p.init_mean = init_mean; p.init_stdev = init_stdev;
+    p.device = device; p.input_space = EALS_HOST;
+    Flat f = flatten(trainMatrix);
+    check(eals_create(&p, f.row_ptr.data(), f.col_idx.data(), f.rv(), f.col_ptr.data(),
+                      f.row_idx.data(), f.cv(), &h_), "eals_create");
+    check(eals_init_factors(h_), "eals_init_factors");   // U.init, V.init, initS (MF_fastALS.cpp:85-90)
+  }
+  ~MF_fastALS_T() { eals_destroy(h_); }
+  MF_fastALS_T(const MF_fastALS_T&) = delete;
+  MF_fastALS_T& operator=(const MF_fastALS_T&) = delete;
+
+  void setTrain(const SparseMatT& trainMatrix) {   // MF_fastALS.cpp:94-104
+    Flat f = flatten(trainMatrix);
+    check(eals_set_train(h_, EALS_HOST, f.row_ptr.data(), f.col_idx.data(), f.rv(),
+                         f.col_ptr.data(), f.row_idx.data(), f.cv()), "eals_set_train");
+  }
+  // MF_fastALS.cpp:106-110, working: dense row-major [userCount][factors] / [itemCount][factors].
+  void setUV(const double* U, const double* V) { check(eals_set_factors(h_, EALS_HOST, U, V), "eals_set_factors"); }
+  // same from DenseMat-like objects exposing double** matrix
+  template <class DenseMatT>
+  void setUV(const DenseMatT& U, const DenseMatT& V) {
+    std::vector<double> u((size_t)userCount * factors), v((size_t)itemCount * factors);
+    for (int r = 0; r < userCount; r++) for (int c = 0; c < factors; c++) u[(size_t)r * factors + c] = U.matrix[r][c];
+    for (int r = 0; r < itemCount; r++) for (int c = 0; c < factors; c++) v[(size_t)r * factors + c] = V.matrix[r][c];
+    setUV(u.data(), v.data());
+  }
+  void getUV(double* U, double* V) { check(eals_get_factors(h_, EALS_HOST, U, V), "eals_get_factors"); }
+  void getS(double* SU, double* SV) { check(eals_get_S(h_, EALS_HOST, SU, SV), "eals_get_S"); }
+
+  // one half-epoch each (MF_fastALS.cpp:127-132, 146-152)
+  void update_user() { check(eals_update_user(h_), "eals_update_user"); }
+  void update_item() { check(eals_update_item(h_), "eals_update_item"); }
+
+  void buildModel() {   // MF_fastALS.cpp:112-161
+    double loss_pre = DBL_MAX;
+    for (int iter = 0; iter < maxIter; iter++) {
+      auto t0 = std::chrono::steady_clock::now();
+      update_user();
+      check(eals_sync(h_), "eals_sync");
+      const double t_user = seconds_since(t0);
+      std::cout << "Time of user_update: " << t_user << std::endl;
+      t0 = std::chrono::steady_clock::now();
+      update_item();
+      check(eals_sync(h_), "eals_sync");
+      const double t_item = seconds_since(t0);
+      std::cout << "Time of item_update: " << t_item << std::endl;
+      if (showloss) loss_pre = showLoss(iter, t_user + t_item, loss_pre);
+    }
+  }
+  void runOneIteration() { update_user(); update_item(); }
+
+  double showLoss(int iter, double time, double loss_pre) {   // MF_fastALS.cpp:175-182
+    auto t0 = std::chrono::steady_clock::now();
+    const double loss_cur = loss();
+    const std::string symbol = loss_pre >= loss_cur ? "-" : "+";
+    std::cout << "Iter=" << iter << " " << time << " " << symbol << " loss:" << loss_cur << " "
+              << seconds_since(t0) << std::endl;
+    return loss_cur;
+  }
+  double loss() { double l = 0; check(eals_loss(h_, &l), "eals_loss"); return l; }
+  double predict(int u, int i) { double s = 0; check(eals_predict(h_, u, i, &s), "eals_predict"); return s; }
+
+  // MF_fastALS.cpp:620-662 — {hit ratio, NDCG, reciprocal rank}; reproduces the reference's ranking
+  // (int-truncating comparator) unless exact is set.
+  std::vector<double> evaluate_for_user(int u, int gtItem, int topK_, bool exact = false) {
+    std::vector<double> r(3);
+    check(eals_evaluate_user(h_, u, gtItem, topK_, exact ? EALS_EVAL_EXACT : EALS_EVAL_REFERENCE, r.data()),
+          "eals_evaluate_user");
+    return r;
+  }
+  // evaluate_model (main.cpp:37-65) over all users at once: means of the three metrics.
+  std::vector<double> evaluate(bool exact = false) {
+    std::vector<int32_t> gt((size_t)userCount);
+    for (int u = 0; u < userCount; u++) gt[u] = testRatings[u].itemId;
+    std::vector<double> s(3);
+    check(eals_evaluate(h_, gt.data(), topK, exact ? EALS_EVAL_EXACT : EALS_EVAL_REFERENCE, s.data(), nullptr,
+                        nullptr, nullptr, nullptr), "eals_evaluate");
+    for (double& x : s) x /= userCount;
+    return s;
+  }
+
+  void update_user_thread(int u) { check(eals_update_user_row(h_, u), "eals_update_user_row"); }
+  void update_item_thread(int i) { check(eals_update_item_row(h_, i), "eals_update_item_row"); }
+  void update_user_SU(double* oldVector, double* uget) { check(eals_patch_SU(h_, oldVector, uget), "eals_patch_SU"); }
+  void update_item_SV(int i, double* oldVector, double* vget) { check(eals_patch_SV(h_, i, oldVector, vget), "eals_patch_SV"); }
+
+  // metric helpers (MF_fastALS.cpp:597-618)
+  double getHitRatio(const std::vector<int>& rankList, int gtItem) {
+    for (int item : rankList) if (item == gtItem) return 1;
+    return 0;
+  }
+  double getNDCG(const std::vector<int>& rankList, int gtItem) {
+    for (size_t i = 0; i < rankList.size(); i++) if (rankList[i] == gtItem) return std::log(2) / std::log(i + 2);
+    return 0;
+  }
+  double getPrecision(const std::vector<int>& rankList, int gtItem) {
+    for (size_t i = 0; i < rankList.size(); i++) if (rankList[i] == gtItem) return 1.0 / (i + 1);
+    return 0;
+  }
+
+  eals_model* handle() { return h_; }
+
+ private:
+  struct Flat {
+    std::vector<int64_t> row_ptr, col_ptr;
+    std::vector<int32_t> col_idx, row_idx;
+    std::vector<double> row_val, col_val;
+    bool ones = true;   // every stored rating is exactly 1 (what the reference's loader writes)
+    const double* rv() const { return ones ? nullptr : row_val.data(); }
+    const double* cv() const { return ones ? nullptr : col_val.data(); }
+  };
+  // rows[u] / cols[i] -> offsets + indices + values, in the stored order (main.cpp:198-205 fills rows
+  // ascending by item and cols ascending by user; eals_create verifies that).
+  static Flat flatten(const SparseMatT& m) {
+    Flat f;
+    const int M = m.n_r, N = m.n_c;
+    f.row_ptr.assign((size_t)M + 1, 0);
+    f.col_ptr.assign((size_t)N + 1, 0);
+    for (int u = 0; u < M; u++) f.row_ptr[u + 1] = f.row_ptr[u] + m.rows[u].n;
+    for (int i = 0; i < N; i++) f.col_ptr[i + 1] = f.col_ptr[i] + m.cols[i].n;
+    f.col_idx.resize((size_t)f.row_ptr[M]); f.row_val.resize((size_t)f.row_ptr[M]);
+    f.row_idx.resize((size_t)f.col_ptr[N]); f.col_val.resize((size_t)f.col_ptr[N]);
+    for (int u = 0; u < M; u++)
+      for (int j = 0; j < m.rows[u].n; j++) {
+        f.col_idx[(size_t)f.row_ptr[u] + j] = m.rows[u].spv_in[j];
+        f.row_val[(size_t)f.row_ptr[u] + j] = m.rows[u].spv_do[j];
+        f.ones &= m.rows[u].spv_do[j] == 1.0;
+      }
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j < m.cols[i].n; j++) {
+        f.row_idx[(size_t)f.col_ptr[i] + j] = m.cols[i].spv_in[j];
+        f.col_val[(size_t)f.col_ptr[i] + j] = m.cols[i].spv_do[j];
+        f.ones &= m.cols[i].spv_do[j] == 1.0;
+      }
+    return f;
+  }
+  static double seconds_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+
+  eals_model* h_ = nullptr;
+};
+
+}  // namespace eals_b200
+#endif

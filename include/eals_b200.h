@@ -178,14 +178,18 @@ int eals_leading_dim(const eals_model* m);                 /* ld of U/V/SU/SV ro
 int eals_device_buffer(eals_model* m, int32_t which, void** dev_ptr, int64_t* bytes);
 int eals_stream(eals_model* m, void** cuda_stream);        /* cudaStream_t the model enqueues on  */
 /* Make the model enqueue on a caller-owned stream (e.g. the one the host's NCCL calls are ordered
- * against); NULL restores the model's own stream.  Synchronises the old stream first. */
-int eals_set_stream(eals_model* m, void* cuda_stream);
+ * against; NULL is the legacy default stream), or back on its own stream when restore_own != 0.
+ * Synchronises the old stream first. */
+int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own);
 int eals_sync(eals_model* m);
 int64_t eals_nnz(const eals_model* m);                     /* nonzeros of the owned user rows     */
 int64_t eals_kernel_launches(const eals_model* m);         /* kernels launched so far             */
 /* Device milliseconds of the most recent call of each kind: [0] user sweep, [1] user Gram,
  * [2] item sweep, [3] item Gram, [4] loss, [5] evaluate.  Synchronises. */
 int eals_timings(eals_model* m, double ms[6]);
+/* Device milliseconds and call counts of every call since the last reset, same six slots; each call
+ * is bracketed by CUDA events on the model's stream, nothing synchronises until this query. */
+int eals_timings_total(eals_model* m, double ms[6], int64_t calls[6], int32_t reset);
 
 #ifdef __cplusplus
 }

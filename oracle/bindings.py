@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -28,7 +29,8 @@ _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 
 def build(target: str = "all") -> None:
     """Run oracle/Makefile (``ref`` is a no-op on a box without /root/reference)."""
-    subprocess.run(["make", "-s", "-C", HERE, target], check=True)
+    # make's chatter goes to stderr: bench.py prints exactly one JSON line on stdout
+    subprocess.run(["make", "-s", "-C", HERE, target], check=True, stdout=sys.stderr)
 
 
 def _opt(arr, dtype):

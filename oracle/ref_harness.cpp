@@ -18,6 +18,9 @@
 // The reference object is deliberately leaked / never copied: its destructor double-frees when a
 // copy exists (main.cpp:37, MF_fastALS.cpp:664-673).
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -52,11 +55,21 @@ SparseMat build_sparse(int M, int N, const int64_t* row_ptr, const int32_t* col_
   return sm;
 }
 
-struct CoutSilencer {
-  std::ostringstream sink;   // declared (hence constructed) before `old`, whose initialiser uses it
-  std::streambuf* old;
-  CoutSilencer() : old(std::cout.rdbuf(sink.rdbuf())) {}
-  ~CoutSilencer() { std::cout.rdbuf(old); }
+// Silences the reference's std::cout chatter by pointing fd 1 at /dev/null for the scope.
+struct StdoutSilencer {
+  int saved;
+  StdoutSilencer() {
+    std::cout.flush();
+    fflush(stdout);
+    saved = dup(1);
+    int nul = open("/dev/null", O_WRONLY);
+    if (nul >= 0) { dup2(nul, 1); close(nul); }
+  }
+  ~StdoutSilencer() {
+    std::cout.flush();
+    fflush(stdout);
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+  }
 };
 
 }  // namespace
@@ -170,7 +183,7 @@ void ref_build_model(void* h, int iters) {
   r->fals->maxIter = iters;
   bool keep = r->fals->showloss;
   r->fals->showloss = false;
-  CoutSilencer quiet;
+  StdoutSilencer quiet;
   r->fals->buildModel();
   r->fals->showloss = keep;
 }

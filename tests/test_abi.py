@@ -65,3 +65,37 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "eals_oracle" not in src and "libeals_ref" not in src, f
+
+
+def test_dropin_class_compiles_against_reference_containers(tmp_path):
+    """The three call sites of main.cpp:227-231,49 compile against include/MF_fastALS.h when the
+    reference's own SparseMat / Rating headers are used (compile-only; needs /root/reference)."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "SparseMat.h")):
+        pytest.skip("reference headers not present on this box")
+    src = tmp_path / "dropin.cpp"
+    src.write_text('''
+#include "SparseMat.h"
+#include "Rating.h"
+#include "MF_fastALS.h"
+using MF_fastALS = eals_b200::MF_fastALS_T<SparseMat, Rating>;
+int run(SparseMat& trainMatrix, std::vector<Rating>& testRatings, int userCount, int itemCount) {
+  MF_fastALS fals(trainMatrix, testRatings, 10, 1, 64, 20, 10, 0.75, 0.01, 0, 0.01, false, true, userCount, itemCount);
+  fals.buildModel();
+  std::vector<double> r = fals.evaluate_for_user(0, testRatings[0].itemId, 10);
+  double l = fals.loss() + fals.predict(0, 0);
+  fals.update_user_thread(0); fals.update_item_thread(0);
+  return (int)(r[0] + l);
+}
+''')
+    # the reference dir is searched AFTER ours so that "MF_fastALS.h" resolves to the drop-in
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", os.path.join(ROOT, "include"), "-idirafter", ref, str(src)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+
+
+def test_cpp_driver_builds():
+    from eals_cpp_b200 import build as b
+    exe = b.build_host_example()
+    assert exe and os.path.exists(exe)
