@@ -1,0 +1,564 @@
+// cd_block.cuh — K1 for long rows: BLOCKED coordinate descent.
+//
+// Same arithmetic as MF_fastALS::update_user_thread / update_item_thread (MF_fastALS.cpp:243-322,
+// 338-407), reorganised so that a row needs ONE team-wide reduction per block of 16 factors instead
+// of one per factor.  For a block B = {f0..f0+15} of the row x, with the prediction cache p_j
+// (current <x, y_j>) at the start of the block:
+//
+//   z_j  = w_j r_j - c_j p_j                        c_j = w_j - Wi[item]
+//   P_f  = sum_j z_j y_jf                           (f in B)
+//   G_kf = sum_j c_j y_jk y_jf                      (k, f in B; the row's local 16 x 16 Gram)
+//   t_f  = sum_k x_k S[f][k]                        (all K, x at the start of the block)
+//   H_kf = G_kf + g S[k][f]                         g = 1 (user side) | Wi[row] (item side)
+//
+// the reference's sequential updates inside the block are, exactly,
+//
+//   for f in B (ascending):  numer = P_f - g t_f + x_f H_ff - sum_{k in B, k < f} d_k H_kf
+//                            x_f'  = numer / (H_ff + reg) ;  d_f = x_f' - x_f
+//
+// (substitute p_j(current) = p_j + sum_{k<f} d_k y_jk into :297-305 and collect terms), followed by
+// p_j += sum_{f in B} d_f y_jf.  Only the floating-point summation order differs.
+//
+// G is GEMM-shaped (16 x n times n x 16) and goes to the fp64 tensor cores
+// (mma.sync.m8n8k4.f64, three 8 x 8 tiles: the upper-right one follows by symmetry); P, the
+// prediction-cache update and the 16-step solve are plain fp64.
+//
+// Data movement: the 128-byte line [f0, f0+16) of every gathered row is copied global -> shared with
+// cp.async (16 B per lane, 8 lanes per line: whole lines, no register staging), XOR-swizzled in
+// 16-byte chunks so that both the per-nonzero row reads (LDS.128) and the tensor-core fragment reads
+// are (nearly) conflict-free.
+//
+// Two drivers share the device code:
+//   * cd_row_block_kernel  — one CTA per row of 129..1024 nonzeros, everything on chip.
+//   * heavy_* kernels      — rows of any length split into slabs of 512 nonzeros; per block one
+//                            launch for the slab partials (+ the deferred cache update of the previous
+//                            block) and one for the per-row solve; prediction cache in HBM.
+#pragma once
+
+#include "cd_sweep.cuh"
+#include "common.cuh"
+
+namespace eals {
+
+constexpr int kBlkThreads = 256;
+constexpr int kBlkWarps = kBlkThreads / 32;
+constexpr int kPartLen = 208;   // 3 tiles x 32 lanes x 2 (C fragments) + 16 (P)
+constexpr int kSlab = 512;      // nonzeros per slab of a heavy row
+
+// ---- swizzled tile: row r = 128 bytes, 16-byte chunk c stored at chunk position c ^ (r & 7) ----
+__device__ __forceinline__ uint32_t tile_chunk_off(int r, int c) { return (uint32_t)(r * 128 + (((c ^ r) & 7) << 4)); }
+__device__ __forceinline__ double tile_elem(const unsigned char* tile, int r, int e) {
+  return *reinterpret_cast<const double*>(tile + tile_chunk_off(r, e >> 1) + ((e & 1) << 3));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Stage factor block fb of the rows idx_s[0..n) into the tile; rows [n, n_pad) are zero-filled.
+template <int LD>
+__device__ __forceinline__ void stage_tile_async(unsigned char* tile, const int* idx_s, const double* __restrict__ Y,
+                                                 int n, int n_pad, int fb, int tid, int nthreads) {
+  for (int q = tid; q < n_pad * 8; q += nthreads) {
+    const int r = q >> 3, c = q & 7;
+    const bool live = r < n;
+    const double* src = live ? Y + (size_t)idx_s[r] * LD + fb * kFB + c * 2 : Y;
+    cp_async16(tile + tile_chunk_off(r, c), src, live ? 16 : 0);
+  }
+}
+
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Sum v[0..16) over the warp; afterwards lanes 2f and 2f+1 hold the total of v[f] (returned).
+__device__ __forceinline__ double warp_reduce16(double (&v)[16]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const bool hi = lane & 16;
+    const double send = hi ? v[i] : v[i + 8];
+    const double keep = hi ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(kFullMask, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const bool hi = lane & 8;
+    const double send = hi ? v[i] : v[i + 4];
+    const double keep = hi ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(kFullMask, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const bool hi = lane & 4;
+    const double send = hi ? v[i] : v[i + 2];
+    const double keep = hi ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(kFullMask, send, 4);
+  }
+  {
+    const bool hi = lane & 2;
+    const double send = hi ? v[0] : v[1];
+    const double keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(kFullMask, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(kFullMask, v[0], 1);
+}
+
+// One warp accumulates the Gram fragments of tile rows [r0, r1) (r0 a multiple of 4; rows past the
+// live count are zero with c = 0).  frag[0..1] = C00, [2..3] = C10, [4..5] = C11.
+__device__ __forceinline__ void gram_fragments(const unsigned char* tile, const double* c_s, int r0, int r1,
+                                               double (&frag)[6]) {
+  const int lane = lane_id();
+  const int rr = lane & 3, e0 = lane >> 2;
+  for (int j0 = r0; j0 < r1; j0 += 4) {
+    const int r = j0 + rr;
+    const double a0 = tile_elem(tile, r, e0);
+    const double a1 = tile_elem(tile, r, 8 + e0);
+    const double cj = c_s[r];
+    const double b0 = cj * a0, b1 = cj * a1;
+    dmma_884(frag[0], frag[1], a0, b0);
+    dmma_884(frag[2], frag[3], a1, b0);
+    dmma_884(frag[4], frag[5], a1, b1);
+  }
+}
+
+// Load the 16 doubles of tile row r into registers.
+__device__ __forceinline__ void load_tile_row(const unsigned char* tile, int r, double (&y)[16]) {
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const double2 d = *reinterpret_cast<const double2*>(tile + tile_chunk_off(r, c));
+    y[2 * c] = d.x;
+    y[2 * c + 1] = d.y;
+  }
+}
+
+// Scatter a summed partial (fragment layout) into the full symmetric Gs[16][16] and Pt[16].
+__device__ __forceinline__ void scatter_partial(int i, double v, double* Gs, double* Pt) {
+  if (i < 192) {
+    const int t = i >> 6, l = (i & 63) >> 1, ii = i & 1;
+    int row = l >> 2, col = 2 * (l & 3) + ii;
+    if (t >= 1) row += 8;
+    if (t == 2) col += 8;
+    Gs[row * 16 + col] = v;
+    if (t == 1) Gs[col * 16 + row] = v;
+  } else if (i < kPartLen) {
+    Pt[i - 192] = v;
+  }
+}
+
+// The per-row, per-block solve, by ONE warp.  x_s: the row's K factors (shared, updated in place);
+// Gs/Pt: summed Gram and right-hand side of the block; delta_s[16] receives d_f.
+template <int LD>
+__device__ __forceinline__ void solve_block(double* x_s, const double* Gs, const double* Pt, double* delta_s,
+                                            const double* __restrict__ S, int f0, int K, double g, double reg) {
+  const int lane = lane_id();
+  // t_f = sum_k x_k S[f0+f][k], k split over lanes; folded with P into base_f = P_f - g t_f
+  double bp[16];
+#pragma unroll
+  for (int f = 0; f < 16; f++) bp[f] = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const double xk = x_s[k];
+#pragma unroll
+    for (int f = 0; f < 16; f++) bp[f] += xk * __ldg(S + (size_t)(f0 + f) * LD + k);
+  }
+#pragma unroll
+  for (int f = 0; f < 16; f++) bp[f] = (lane == 0 ? Pt[f] : 0.0) - g * bp[f];
+  const double base_pair = warp_reduce16(bp);                       // lanes 2f, 2f+1 hold base_f
+  const int f = lane & 15;
+  const double base = __shfl_sync(kFullMask, base_pair, 2 * f);
+  double h[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + f] + g * __ldg(S + (size_t)(f0 + k) * LD + f0 + f);
+  const double xf = x_s[f0 + f];
+  double hff = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) hff = (k == f) ? h[k] : hff;
+  double numer = base + xf * hff;
+  const double denom = hff + reg;
+  double xnew = xf, mydelta = 0.0;
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    const double cand = numer / denom;
+    const double d = cand - xf;
+    const double ds = __shfl_sync(kFullMask, d, s);
+    if (f == s) { xnew = cand; mydelta = d; }
+    if (f > s) numer -= ds * h[s];
+  }
+  if (lane < 16) {
+    if (f0 + f < K) x_s[f0 + f] = xnew;
+    delta_s[f] = (f0 + f < K) ? mydelta : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One CTA per row, 129 .. 256*MW nonzeros.  Thread t owns nonzeros t, t+256, ...; warp w feeds tile
+// rows [w*32*MW, (w+1)*32*MW) to the tensor cores.
+// ---------------------------------------------------------------------------------------------
+template <int LD, int MW>
+struct RowBlockSmem {
+  static constexpr int kRows = kBlkThreads * MW;
+  static constexpr size_t kTile = (size_t)kRows * 128;
+  static constexpr size_t kIdx = (size_t)kRows * 4;
+  static constexpr size_t kC = (size_t)kRows * 8;
+  static constexpr size_t kX = (size_t)LD * 8;
+  static constexpr size_t kSlots = (size_t)kBlkWarps * kPartLen * 8;
+  static constexpr size_t kSmall = (256 + 16 + 16) * 8;
+  static constexpr size_t kBytes = kTile + kIdx + kC + kX + kSlots + kSmall;
+};
+
+template <int LD, int MW, bool USER>
+__global__ void __launch_bounds__(kBlkThreads)
+cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using Sm = RowBlockSmem<LD, MW>;
+  unsigned char* tile = smem;
+  int* idx_s = reinterpret_cast<int*>(smem + Sm::kTile);
+  double* c_s = reinterpret_cast<double*>(smem + Sm::kTile + Sm::kIdx);
+  double* x_s = c_s + Sm::kRows;
+  double* slots = x_s + LD;
+  double* Gs = slots + kBlkWarps * kPartLen;
+  double* Pt = Gs + 256;
+  double* delta_s = Pt + 16;
+
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int row = order[first + blockIdx.x];
+  const int64_t p0 = a.ptr[row];
+  const int n = (int)(a.ptr[row + 1] - p0);
+  const int n_pad = (n + 3) & ~3;
+  const int grow = a.row_base + row;
+  double* xrow = a.X + (size_t)grow * LD;
+  const int K = a.K;
+  const double wi_row = USER ? 0.0 : a.Wi[grow];
+  const double g = USER ? 1.0 : wi_row;
+
+  double pr[MW], cw[MW], wr[MW];
+#pragma unroll
+  for (int m = 0; m < MW; m++) {
+    const int j = m * kBlkThreads + tid;
+    pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
+    if (j < n) {
+      const int id = a.idx[p0 + j];
+      idx_s[j] = id;
+      const double w = a.val ? a.val[p0 + j] : 1.0;
+      wr[m] = w * w;
+      cw[m] = w - (USER ? a.Wi[id] : wi_row);
+    }
+    if (j < Sm::kRows) c_s[j] = cw[m];
+  }
+  for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
+  __syncthreads();
+
+  const int nblocks = (K + kFB - 1) / kFB;
+
+  // Pass 1: prediction cache p_j = <x, y_j>
+  for (int fb = 0; fb < nblocks; fb++) {
+    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MW; m++) {
+      const int j = m * kBlkThreads + tid;
+      if (j < n) {
+        double y[16];
+        load_tile_row(tile, j, y);
+        double acc = pr[m];
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc += x_s[fb * kFB + e] * y[e];
+        pr[m] = acc;
+      }
+    }
+    __syncthreads();
+  }
+
+  // Pass 2: one blocked update per 16 factors
+  const int w_r0 = warp * 32 * MW;
+  const int w_r1 = min(w_r0 + 32 * MW, n_pad);
+  for (int fb = 0; fb < nblocks; fb++) {
+    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    double pp[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) pp[e] = 0.0;
+#pragma unroll
+    for (int m = 0; m < MW; m++) {
+      const int j = m * kBlkThreads + tid;
+      if (j < n) {
+        double y[16];
+        load_tile_row(tile, j, y);
+        const double z = wr[m] - cw[m] * pr[m];
+#pragma unroll
+        for (int e = 0; e < 16; e++) pp[e] += z * y[e];
+      }
+    }
+    const double ptot = warp_reduce16(pp);
+    double frag[6] = {0, 0, 0, 0, 0, 0};
+    gram_fragments(tile, c_s, w_r0, w_r1, frag);
+    double* slot = slots + warp * kPartLen;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      slot[t * 64 + lane * 2] = frag[2 * t];
+      slot[t * 64 + lane * 2 + 1] = frag[2 * t + 1];
+    }
+    if ((lane & 1) == 0) slot[192 + (lane >> 1)] = ptot;
+    __syncthreads();
+    if (tid < kPartLen) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBlkWarps; w++) s += slots[w * kPartLen + tid];
+      scatter_partial(tid, s, Gs, Pt);
+    }
+    __syncthreads();
+    if (warp == 0) solve_block<LD>(x_s, Gs, Pt, delta_s, a.S, fb * kFB, K, g, a.reg);
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MW; m++) {
+      const int j = m * kBlkThreads + tid;
+      if (j < n) {
+        double y[16];
+        load_tile_row(tile, j, y);
+        double acc = pr[m];
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc += delta_s[e] * y[e];
+        pr[m] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < K; k += kBlkThreads) xrow[k] = x_s[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Heavy rows: slabs of kSlab nonzeros, prediction cache in HBM (a compact array per side), one
+// launch pair per factor block over a BATCH of rows small enough that the block's lines stay in L2
+// between the partials launch and the deferred cache update of the next one.
+// ---------------------------------------------------------------------------------------------
+struct HeavyUnits {
+  const int32_t* unit_row;     // owned-row id of the unit
+  const int32_t* unit_hrow;    // index of that row among the heavy rows (delta / x slots)
+  const int64_t* unit_off;     // offset of the unit's first nonzero in the side's idx/val arrays
+  const int64_t* unit_poff;    // offset of the same nonzero in the compact prediction cache
+  const int32_t* unit_cnt;     // nonzeros in the unit (<= kSlab)
+  const int32_t* hrow_id;      // owned-row id of heavy row h
+  const int32_t* hrow_unit0;   // first unit of heavy row h
+  const int32_t* hrow_units;   // number of units of heavy row h
+};
+
+// p_j = <x_row, y_j> for every nonzero of the units [u0, u0 + gridDim.x): 8 lanes per nonzero.
+template <int LD>
+__global__ void __launch_bounds__(kBlkThreads)
+heavy_pred_kernel(CdSide a, HeavyUnits hu, int u0, double* __restrict__ pred) {
+  __shared__ double x_s[LD];
+  const int tid = threadIdx.x;
+  const int u = u0 + blockIdx.x;
+  const int row = hu.unit_row[u];
+  const double* xrow = a.X + (size_t)(a.row_base + row) * LD;
+  for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
+  __syncthreads();
+  const int64_t off = hu.unit_off[u], poff = hu.unit_poff[u];
+  const int cnt = hu.unit_cnt[u];
+  const int g8 = tid >> 3, gl = tid & 7;
+  for (int j0 = 0; j0 < cnt; j0 += kBlkThreads / 8) {
+    const int j = j0 + g8;
+    double acc = 0.0;
+    if (j < cnt) {
+      const double* yrow = a.Y + (size_t)a.idx[off + j] * LD;
+#pragma unroll
+      for (int c = 0; c < LD; c += kFB) {
+        const double2 d = ldg2(yrow + c + gl * 2);
+        acc += x_s[c + gl * 2] * d.x;
+        acc += x_s[c + gl * 2 + 1] * d.y;
+      }
+    }
+    acc += __shfl_xor_sync(kFullMask, acc, 1);
+    acc += __shfl_xor_sync(kFullMask, acc, 2);
+    acc += __shfl_xor_sync(kFullMask, acc, 4);
+    if (j < cnt && gl == 0) pred[poff + j] = acc;
+  }
+}
+
+struct HeavySmem {
+  static constexpr size_t kTile = (size_t)kSlab * 128;
+  static constexpr size_t kIdx = (size_t)kSlab * 4;
+  static constexpr size_t kC = (size_t)kSlab * 8;
+  static constexpr size_t kSlots = (size_t)kBlkWarps * kPartLen * 8;
+  static constexpr size_t kBytes = kTile + kIdx + kC + kSlots + 16 * 8;
+};
+
+// Step fb of the batch: (1) if fb > 0, apply the cache update of block fb-1 (needs that block's
+// lines again — L2-resident by the batching) ; (2) if fb < nblocks, form the slab's partial Gram and
+// right-hand side of block fb and write them to partials[unit - u0].
+template <int LD, bool USER>
+__global__ void __launch_bounds__(kBlkThreads)
+heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* __restrict__ pred,
+                  const double* __restrict__ delta, double* __restrict__ partials) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* tile = smem;
+  int* idx_s = reinterpret_cast<int*>(smem + HeavySmem::kTile);
+  double* c_s = reinterpret_cast<double*>(smem + HeavySmem::kTile + HeavySmem::kIdx);
+  double* slots = c_s + kSlab;
+  double* delta_s = slots + kBlkWarps * kPartLen;
+  constexpr int MW = kSlab / kBlkThreads;
+
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int u = u0 + blockIdx.x;
+  const int row = hu.unit_row[u];
+  const int64_t off = hu.unit_off[u], poff = hu.unit_poff[u];
+  const int n = hu.unit_cnt[u];
+  const int n_pad = (n + 3) & ~3;
+  const int grow = a.row_base + row;
+  const double wi_row = USER ? 0.0 : a.Wi[grow];
+
+  double pr[MW], cw[MW], wr[MW];
+#pragma unroll
+  for (int m = 0; m < MW; m++) {
+    const int j = m * kBlkThreads + tid;
+    pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
+    if (j < n) {
+      const int id = a.idx[off + j];
+      idx_s[j] = id;
+      const double w = a.val ? a.val[off + j] : 1.0;
+      wr[m] = w * w;
+      cw[m] = w - (USER ? a.Wi[id] : wi_row);
+      pr[m] = pred[poff + j];
+    }
+    c_s[j] = cw[m];
+  }
+  if (fb > 0 && tid < 16) delta_s[tid] = delta[(size_t)hu.unit_hrow[u] * 16 + tid];
+  __syncthreads();
+
+  if (fb > 0) {
+    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb - 1, tid, kBlkThreads);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MW; m++) {
+      const int j = m * kBlkThreads + tid;
+      if (j < n) {
+        double y[16];
+        load_tile_row(tile, j, y);
+        double acc = pr[m];
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc += delta_s[e] * y[e];
+        pr[m] = acc;
+        pred[poff + j] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (fb >= nblocks) return;
+
+  stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  double pp[16];
+#pragma unroll
+  for (int e = 0; e < 16; e++) pp[e] = 0.0;
+#pragma unroll
+  for (int m = 0; m < MW; m++) {
+    const int j = m * kBlkThreads + tid;
+    if (j < n) {
+      double y[16];
+      load_tile_row(tile, j, y);
+      const double z = wr[m] - cw[m] * pr[m];
+#pragma unroll
+      for (int e = 0; e < 16; e++) pp[e] += z * y[e];
+    }
+  }
+  const double ptot = warp_reduce16(pp);
+  double frag[6] = {0, 0, 0, 0, 0, 0};
+  const int w_r0 = warp * 32 * MW;
+  gram_fragments(tile, c_s, w_r0, min(w_r0 + 32 * MW, n_pad), frag);
+  double* slot = slots + warp * kPartLen;
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    slot[t * 64 + lane * 2] = frag[2 * t];
+    slot[t * 64 + lane * 2 + 1] = frag[2 * t + 1];
+  }
+  if ((lane & 1) == 0) slot[192 + (lane >> 1)] = ptot;
+  __syncthreads();
+  if (tid < kPartLen) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBlkWarps; w++) s += slots[w * kPartLen + tid];
+    partials[(size_t)(u - u0) * kPartLen + tid] = s;
+  }
+}
+
+// Level-2 reduction for rows with very many units: out[g] = sum of the 32 unit partials of group g.
+__global__ void __launch_bounds__(kBlkThreads)
+heavy_reduce_kernel(const double* __restrict__ partials, int nu, double* __restrict__ out) {
+  const int tid = threadIdx.x;
+  if (tid >= kPartLen) return;
+  const int q0 = blockIdx.x * 32, q1 = min(q0 + 32, nu);
+  double s = 0.0;
+  for (int q = q0; q < q1; q++) s += partials[(size_t)q * kPartLen + tid];
+  out[(size_t)blockIdx.x * kPartLen + tid] = s;
+}
+
+// One CTA per heavy row of the batch: add the row's partials in a fixed order (8 warps take every
+// 8th entry, then the 8 sums are added in warp order), solve block fb, write the new factors and d_f.
+// override_count > 0: the row's partials are partials[0 .. override_count) (level-2 groups).
+template <int LD, bool USER>
+__global__ void __launch_bounds__(kBlkThreads)
+heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int u0, int fb, const double* __restrict__ partials,
+                   int override_count, double* __restrict__ delta) {
+  __shared__ double x_s[LD];
+  __shared__ double Gs[256];
+  __shared__ double Pt[16];
+  __shared__ double delta_s[16];
+  __shared__ double wsum[kBlkWarps][kPartLen];
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int h = h0 + blockIdx.x;
+  const int row = hu.hrow_id[h];
+  const int grow = a.row_base + row;
+  double* xrow = a.X + (size_t)grow * LD;
+  for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
+  const int ufirst = override_count > 0 ? 0 : hu.hrow_unit0[h] - u0;
+  const int ucount = override_count > 0 ? override_count : hu.hrow_units[h];
+  {
+    double acc[7];
+#pragma unroll
+    for (int t = 0; t < 7; t++) acc[t] = 0.0;
+    for (int q = warp; q < ucount; q += kBlkWarps) {
+      const double* p = partials + (size_t)(ufirst + q) * kPartLen;
+#pragma unroll
+      for (int t = 0; t < 7; t++)
+        if (lane + 32 * t < kPartLen) acc[t] += p[lane + 32 * t];
+    }
+#pragma unroll
+    for (int t = 0; t < 7; t++)
+      if (lane + 32 * t < kPartLen) wsum[warp][lane + 32 * t] = acc[t];
+  }
+  __syncthreads();
+  if (tid < kPartLen) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBlkWarps; w++) s += wsum[w][tid];
+    scatter_partial(tid, s, Gs, Pt);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const double g = USER ? 1.0 : a.Wi[grow];
+    solve_block<LD>(x_s, Gs, Pt, delta_s, a.S, fb * kFB, a.K, g, a.reg);
+  }
+  __syncthreads();
+  if (tid < 16) {
+    delta[(size_t)h * 16 + tid] = delta_s[tid];
+    const int k = fb * kFB + tid;
+    if (k < a.K) xrow[k] = x_s[k];
+  }
+}
+
+}  // namespace eals

@@ -170,100 +170,4 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
   for (int k = lane; k < K; k += 32) xrow[k] = u_s[k];
 }
 
-// ---------------------------------------------------------------------------------------------
-// CTA-per-row kernel: rows of ANY length.  The prediction cache is a device-resident fp64 array
-// `e` (one slot per nonzero of the owned rows); every factor step streams the row once, reading
-// the two adjacent factor columns f-1 and f of each gathered row (same 32-byte sector three times
-// out of four) so the cache refresh of step f-1 is folded into step f.
-// ---------------------------------------------------------------------------------------------
-constexpr int kCtaThreads = 256;
-
-template <int LD, bool USER>
-__global__ void __launch_bounds__(kCtaThreads)
-cd_cta_kernel(CdSide a, const int32_t* __restrict__ order, int first,
-              const int64_t* __restrict__ long_ptr, double* __restrict__ e) {
-  __shared__ double u_s[LD];
-  __shared__ double red[2][kCtaThreads / 32][2];
-  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-
-  const int row = order[first + blockIdx.x];
-  const int64_t p0 = a.ptr[row];
-  const int n = (int)(a.ptr[row + 1] - p0);
-  const int grow = a.row_base + row;
-  double* xrow = a.X + (size_t)grow * LD;
-  const int K = a.K;
-  const double wi_row = USER ? 0.0 : a.Wi[grow];
-  const int32_t* __restrict__ idx = a.idx + p0;
-  const double* __restrict__ val = a.val ? a.val + p0 : nullptr;
-  double* __restrict__ er = e + long_ptr[row];
-
-  for (int k = tid; k < LD; k += kCtaThreads) u_s[k] = xrow[k];
-  __syncthreads();
-
-  // Prediction cache: 8 lanes per nonzero, each reading 16 B of every 128 B line of the row.
-  {
-    const int g = tid >> 3, gl = tid & 7;
-    for (int j0 = 0; j0 < n; j0 += kCtaThreads / 8) {
-      const int j = j0 + g;
-      double acc = 0.0;
-      if (j < n) {
-        const double* yrow = a.Y + (size_t)idx[j] * LD;
-#pragma unroll
-        for (int c = 0; c < LD; c += kFB) {
-          const double2 d = ldg2(yrow + c + gl * 2);
-          acc += u_s[c + gl * 2] * d.x;
-          acc += u_s[c + gl * 2 + 1] * d.y;
-        }
-      }
-      acc += __shfl_xor_sync(kFullMask, acc, 1);
-      acc += __shfl_xor_sync(kFullMask, acc, 2);
-      acc += __shfl_xor_sync(kFullMask, acc, 4);
-      if (j < n && gl == 0) er[j] = acc;
-    }
-  }
-  __syncthreads();
-
-  double pend = 0.0;  // x_{f-1} just computed: its cache refresh is applied while streaming step f
-  for (int f = 0; f < K; f++) {
-    const double uf = u_s[f];
-    const double* __restrict__ Srow = a.S + (size_t)f * LD;
-    double np = 0.0, dp = 0.0;
-    for (int k = tid; k < K; k += kCtaThreads)
-      if (k != f) np -= u_s[k] * __ldg(Srow + k);
-    if (!USER) np *= wi_row;
-    for (int j = tid; j < n; j += kCtaThreads) {
-      const int id = idx[j];
-      const double* yrow = a.Y + (size_t)id * LD;
-      const double v = __ldg(yrow + f);
-      double pm = er[j];
-      if (f > 0) pm += pend * __ldg(yrow + f - 1);
-      pm -= uf * v;
-      const double w = val ? val[j] : 1.0;
-      const double c = w - (USER ? __ldg(a.Wi + id) : wi_row);
-      np += (w * w - c * pm) * v;
-      dp += c * v * v;
-      er[j] = pm;
-    }
-    warp_sum_pair(np, dp);
-    if (lane == 0) {
-      red[f & 1][warp][0] = np;
-      red[f & 1][warp][1] = dp;
-    }
-    __syncthreads();
-    double numer = 0.0, denom = 0.0;
-#pragma unroll
-    for (int w = 0; w < kCtaThreads / 32; w++) {
-      numer += red[f & 1][w][0];
-      denom += red[f & 1][w][1];
-    }
-    const double sff = __ldg(Srow + f);
-    denom += (USER ? sff : wi_row * sff) + a.reg;
-    const double unew = numer / denom;
-    pend = unew;
-    if (tid == 0) u_s[f] = unew;
-    __syncthreads();
-  }
-  for (int k = tid; k < K; k += kCtaThreads) xrow[k] = u_s[k];
-}
-
 }  // namespace eals

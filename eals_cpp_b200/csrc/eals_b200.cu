@@ -18,6 +18,7 @@
 #include <utility>
 #include <vector>
 
+#include "cd_block.cuh"
 #include "cd_sweep.cuh"
 #include "common.cuh"
 #include "eval.cuh"
@@ -59,9 +60,16 @@ int dev_alloc(T** p, size_t n) {
 }
 
 // Buckets of owned rows by length.  Bucket 0 = empty rows (skipped: MF_fastALS.cpp:249,344).
-constexpr int kNumBuckets = 5;
-constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 128, 0x7fffffff};
-constexpr int kLongBucket = 4;
+// 1..3: warp per row (1/2/4 nonzeros per lane); 4..6: one CTA per row, blocked CD (1/2/4 nonzeros
+// per thread); 7: heavy rows, split into slabs.
+constexpr int kNumBuckets = 8;
+constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 128, 256, 512, 1024, 0x7fffffff};
+constexpr int kMidBucket = 4;     // first one-CTA-per-row bucket
+constexpr int kHeavyBucket = 7;
+constexpr int64_t kDefaultBatchNnz = 384 * 1024;   // heavy rows per launch group: one factor block of the
+                                                   // batch (nnz * 128 B = 48 MB) stays L2-resident
+
+struct HeavyBatch { int h0, h1, u0, u1; };
 
 struct Side {
   int rows = 0;       // owned rows
@@ -72,9 +80,17 @@ struct Side {
   double* val = nullptr;
   int32_t* order = nullptr;           // owned-row ids grouped by bucket, ascending id inside
   int first[kNumBuckets + 1] = {0};   // bucket b = order[first[b] .. first[b+1])
-  int64_t* long_ptr = nullptr;        // ptr rebased so that long rows index a compact pred cache
-  int64_t long_nnz = 0;
-  double* pred = nullptr;             // prediction cache of the long rows
+  // heavy rows (bucket 7): row h = order[first[7] + h], longest first
+  int n_hrows = 0, n_units = 0, max_batch_units = 0;
+  int64_t heavy_nnz = 0;
+  int32_t *unit_row = nullptr, *unit_hrow = nullptr, *unit_cnt = nullptr;
+  int64_t *unit_off = nullptr, *unit_poff = nullptr;
+  int32_t *hrow_id = nullptr, *hrow_unit0 = nullptr, *hrow_units = nullptr;
+  std::vector<int32_t> h_hrow_unit0, h_hrow_units;
+  std::vector<int32_t> h_row_to_hrow;  // owned row -> heavy index or -1 (only filled when heavy rows exist)
+  std::vector<HeavyBatch> batches;
+  double* pred = nullptr;             // prediction cache of the heavy rows (compact)
+  double* delta = nullptr;            // [n_hrows][16] factor changes of the current block
   std::vector<int64_t> h_ptr;         // host copy of ptr (rebased to 0)
 };
 
@@ -124,7 +140,9 @@ int check_launch(eals_model* m) {
 
 void free_side(Side& s) {
   cudaFree(s.ptr); cudaFree(s.idx); cudaFree(s.val); cudaFree(s.order);
-  cudaFree(s.long_ptr); cudaFree(s.pred);
+  cudaFree(s.pred); cudaFree(s.delta);
+  cudaFree(s.unit_row); cudaFree(s.unit_hrow); cudaFree(s.unit_cnt); cudaFree(s.unit_off); cudaFree(s.unit_poff);
+  cudaFree(s.hrow_id); cudaFree(s.hrow_unit0); cudaFree(s.hrow_units);
   s = Side();
 }
 
@@ -148,6 +166,8 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ ptr, const int32
     prev = c;
   }
 }
+
+int ensure_partials(eals_model* m, size_t n);
 
 // Upload the owned slice [begin, end) of one orientation of the matrix and bucket its rows.
 int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int space,
@@ -208,26 +228,76 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
   for (int b = 0; b < kNumBuckets; b++) fill[b] = s.first[b];
   for (int r = 0; r < s.rows; r++) order[fill[bucket_of(s.h_ptr[r + 1] - s.h_ptr[r])]++] = r;
   // long rows: longest first, so the tail of the launch is made of the cheapest rows
-  std::stable_sort(order.begin() + s.first[kLongBucket], order.begin() + s.first[kLongBucket + 1],
+  std::stable_sort(order.begin() + s.first[kHeavyBucket], order.begin() + s.first[kHeavyBucket + 1],
                    [&](int a, int b) {
                      return s.h_ptr[a + 1] - s.h_ptr[a] > s.h_ptr[b + 1] - s.h_ptr[b];
                    });
   OK(dev_alloc(&s.order, order.size()));
   CU(cudaMemcpyAsync(s.order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, m->stream));
 
-  // compact prediction cache for the long rows
-  std::vector<int64_t> long_ptr((size_t)s.rows + 1, 0);
-  int64_t acc = 0;
-  for (int r = 0; r < s.rows; r++) {
-    const int64_t n = s.h_ptr[r + 1] - s.h_ptr[r];
-    long_ptr[r] = acc;
-    if (n > kBucketMax[kLongBucket - 1]) acc += n;
+  // heavy rows -> slabs ("units") of kSlab nonzeros and batches of rows
+  {
+    const int hb = s.first[kHeavyBucket], he = s.first[kHeavyBucket + 1];
+    s.n_hrows = he - hb;
+    std::vector<int32_t> unit_row, unit_hrow, unit_cnt, hrow_id;
+    std::vector<int64_t> unit_off, unit_poff;
+    s.h_hrow_unit0.clear(); s.h_hrow_units.clear(); s.batches.clear(); s.h_row_to_hrow.clear();
+    int64_t poff = 0, batch_nnz = 0;
+    int64_t batch_limit = kDefaultBatchNnz;
+    if (const char* e = getenv("EALS_HEAVY_BATCH_NNZ")) batch_limit = std::max<int64_t>(atoll(e), 1);
+    if (s.n_hrows) s.h_row_to_hrow.assign((size_t)s.rows, -1);
+    HeavyBatch cur{0, 0, 0, 0};
+    for (int h = 0; h < s.n_hrows; h++) {
+      const int r = order[hb + h];
+      const int64_t n = s.h_ptr[r + 1] - s.h_ptr[r];
+      if (h > cur.h0 && batch_nnz + n > batch_limit) {
+        cur.h1 = h; cur.u1 = (int)unit_row.size();
+        s.batches.push_back(cur);
+        cur = HeavyBatch{h, h, cur.u1, cur.u1};
+        batch_nnz = 0;
+      }
+      batch_nnz += n;
+      s.h_row_to_hrow[r] = h;
+      hrow_id.push_back(r);
+      s.h_hrow_unit0.push_back((int)unit_row.size());
+      int units = 0;
+      for (int64_t o = 0; o < n; o += eals::kSlab, units++) {
+        unit_row.push_back(r);
+        unit_hrow.push_back(h);
+        unit_off.push_back(s.h_ptr[r] + o);
+        unit_poff.push_back(poff + o);
+        unit_cnt.push_back((int)std::min<int64_t>(eals::kSlab, n - o));
+      }
+      s.h_hrow_units.push_back(units);
+      poff += n;
+    }
+    if (s.n_hrows) {
+      cur.h1 = s.n_hrows; cur.u1 = (int)unit_row.size();
+      s.batches.push_back(cur);
+    }
+    s.n_units = (int)unit_row.size();
+    s.heavy_nnz = poff;
+    s.max_batch_units = 0;
+    for (const auto& b : s.batches) s.max_batch_units = std::max(s.max_batch_units, b.u1 - b.u0);
+    auto up32 = [&](int32_t** d, const std::vector<int32_t>& v) -> int {
+      OK(dev_alloc(d, v.size()));
+      if (!v.empty()) CU(cudaMemcpyAsync(*d, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, m->stream));
+      return EALS_OK;
+    };
+    auto up64 = [&](int64_t** d, const std::vector<int64_t>& v) -> int {
+      OK(dev_alloc(d, v.size()));
+      if (!v.empty()) CU(cudaMemcpyAsync(*d, v.data(), sizeof(int64_t) * v.size(), cudaMemcpyHostToDevice, m->stream));
+      return EALS_OK;
+    };
+    OK(up32(&s.unit_row, unit_row)); OK(up32(&s.unit_hrow, unit_hrow)); OK(up32(&s.unit_cnt, unit_cnt));
+    OK(up64(&s.unit_off, unit_off)); OK(up64(&s.unit_poff, unit_poff));
+    OK(up32(&s.hrow_id, hrow_id)); OK(up32(&s.hrow_unit0, s.h_hrow_unit0)); OK(up32(&s.hrow_units, s.h_hrow_units));
+    OK(dev_alloc(&s.pred, (size_t)s.heavy_nnz));
+    OK(dev_alloc(&s.delta, (size_t)s.n_hrows * 16));
+    CU(cudaStreamSynchronize(m->stream));   // the host vectors above go out of scope
+    // size the partials scratch now: a reallocation in the middle of a sweep would synchronise
+    OK(ensure_partials(m, (size_t)(s.max_batch_units + (s.max_batch_units + 31) / 32 + 2) * eals::kPartLen));
   }
-  long_ptr[s.rows] = acc;
-  s.long_nnz = acc;
-  OK(dev_alloc(&s.long_ptr, long_ptr.size()));
-  CU(cudaMemcpyAsync(s.long_ptr, long_ptr.data(), sizeof(int64_t) * long_ptr.size(), cudaMemcpyHostToDevice, m->stream));
-  OK(dev_alloc(&s.pred, (size_t)s.long_nnz));
   CU(cudaStreamSynchronize(m->stream));
   return EALS_OK;
 }
@@ -327,28 +397,83 @@ int launch_cd_warp(eals_model* m, const CdSide& a, const int32_t* order, int fir
   return check_launch(m);
 }
 
+template <int LD, int MW, bool USER>
+int launch_cd_row_block(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
+  if (count <= 0) return EALS_OK;
+  using Sm = eals::RowBlockSmem<LD, MW>;
+  auto kern = eals::cd_row_block_kernel<LD, MW, USER>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::kBytes));
+  kern<<<count, eals::kBlkThreads, Sm::kBytes, m->stream>>>(a, order, first);
+  return check_launch(m);
+}
+
+eals::HeavyUnits heavy_units(const Side& s) {
+  eals::HeavyUnits hu;
+  hu.unit_row = s.unit_row; hu.unit_hrow = s.unit_hrow; hu.unit_off = s.unit_off; hu.unit_poff = s.unit_poff;
+  hu.unit_cnt = s.unit_cnt; hu.hrow_id = s.hrow_id; hu.hrow_unit0 = s.hrow_unit0; hu.hrow_units = s.hrow_units;
+  return hu;
+}
+
+// One batch of heavy rows: prediction cache, then per factor block a partials launch (which also
+// applies the previous block's cache update) and a solve launch.
+template <int LD, bool USER>
+int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b) {
+  const int nu = b.u1 - b.u0, nh = b.h1 - b.h0;
+  if (nu <= 0) return EALS_OK;
+  const eals::HeavyUnits hu = heavy_units(s);
+  const int nblocks = (m->K + eals::kFB - 1) / eals::kFB;
+  // level-2 partials (one per group of 32 units) live behind the unit partials
+  const int ngroups = (nu + 31) / 32;
+  const bool two_level = nh == 1 && nu > 512;
+  OK(ensure_partials(m, (size_t)(nu + ngroups) * eals::kPartLen));
+  double* part = m->partials;
+  double* part2 = m->partials + (size_t)nu * eals::kPartLen;
+  auto step = eals::heavy_step_kernel<LD, USER>;
+  CU(cudaFuncSetAttribute(step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eals::HeavySmem::kBytes));
+  eals::heavy_pred_kernel<LD><<<nu, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.u0, s.pred);
+  OK(check_launch(m));
+  for (int fb = 0; fb < nblocks; fb++) {
+    step<<<nu, eals::kBlkThreads, eals::HeavySmem::kBytes, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
+    OK(check_launch(m));
+    if (two_level) {
+      eals::heavy_reduce_kernel<<<ngroups, eals::kBlkThreads, 0, m->stream>>>(part, nu, part2);
+      OK(check_launch(m));
+      eals::heavy_solve_kernel<LD, USER><<<nh, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.h0, b.u0, fb, part2, ngroups, s.delta);
+    } else {
+      eals::heavy_solve_kernel<LD, USER><<<nh, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.h0, b.u0, fb, part, 0, s.delta);
+    }
+    OK(check_launch(m));
+  }
+  return EALS_OK;
+}
+
 template <int LD, bool USER>
 int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   if (only_row >= 0) {  // single-row API: a one-entry order list in scratch
     const int64_t n = s.h_ptr[only_row + 1] - s.h_ptr[only_row];
     if (n == 0) return EALS_OK;
+    if (n > kBucketMax[kHeavyBucket - 1]) {
+      const int h = s.h_row_to_hrow[only_row];
+      return run_heavy_batch<LD, USER>(m, s, a, HeavyBatch{h, h + 1, s.h_hrow_unit0[h], s.h_hrow_unit0[h] + s.h_hrow_units[h]});
+    }
     OK(ensure_partials(m, 16));
     int32_t* one = reinterpret_cast<int32_t*>(m->partials);
     CU(cudaMemcpyAsync(one, &only_row, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
     if (n <= 32) return launch_cd_warp<LD, 1, USER>(m, a, one, 0, 1);
     if (n <= 64) return launch_cd_warp<LD, 2, USER>(m, a, one, 0, 1);
     if (n <= 128) return launch_cd_warp<LD, 4, USER>(m, a, one, 0, 1);
-    eals::cd_cta_kernel<LD, USER><<<1, eals::kCtaThreads, 0, m->stream>>>(a, one, 0, s.long_ptr, s.pred);
-    return check_launch(m);
+    if (n <= 256) return launch_cd_row_block<LD, 1, USER>(m, a, one, 0, 1);
+    if (n <= 512) return launch_cd_row_block<LD, 2, USER>(m, a, one, 0, 1);
+    return launch_cd_row_block<LD, 4, USER>(m, a, one, 0, 1);
   }
-  OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
-  OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+  // heavy rows first: their launch chain is the longest
+  for (const HeavyBatch& b : s.batches) OK((run_heavy_batch<LD, USER>(m, s, a, b)));
+  OK((launch_cd_row_block<LD, 4, USER>(m, a, s.order, s.first[6], s.first[7] - s.first[6])));
+  OK((launch_cd_row_block<LD, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));
+  OK((launch_cd_row_block<LD, 1, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
   OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
-  const int nlong = s.first[5] - s.first[4];
-  if (nlong > 0) {
-    eals::cd_cta_kernel<LD, USER><<<nlong, eals::kCtaThreads, 0, m->stream>>>(a, s.order, s.first[4], s.long_ptr, s.pred);
-    OK(check_launch(m));
-  }
+  OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+  OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
   return EALS_OK;
 }
 
@@ -452,8 +577,8 @@ int download_dense(eals_model* m, double* dst, const double* src, size_t n, int 
 
 template <int LD>
 int launch_loss_rows(eals_model* m, const eals::LossSide& a, Side& s, int* n_partials) {
-  const int short_first = s.first[1], short_count = s.first[4] - s.first[1];
-  const int long_first = s.first[4], long_count = s.first[5] - s.first[4];
+  const int short_first = s.first[1], short_count = s.first[kMidBucket] - s.first[1];
+  const int long_first = s.first[kMidBucket], long_count = s.first[kNumBuckets] - s.first[kMidBucket];
   const int g_short = short_count ? std::min((short_count + 7) / 8, 8 * m->sm_count) : 0;
   const int g_long = long_count ? std::min(long_count, 8 * m->sm_count) : 0;
   OK(ensure_partials(m, (size_t)std::max(1, g_short + g_long)));

@@ -76,11 +76,23 @@ def _item_cdf(rng, N, zipf, col_cap_frac=None):
     return np.cumsum(p), perm
 
 
-def powerlaw_csr(M, N, nnz, sigma=1.0, clip=(1, 4000), zipf=0.9, seed=0, **_) -> Interactions:
+def powerlaw_csr(M, N, nnz, sigma=1.0, clip=(1, 4000), zipf=0.9, seed=0, calibrate=2, **_) -> Interactions:
     """Host generator. Draw degree+1 items per user (with replacement), dedup, hold the last
-    distinct draw out as the test item when the user has more than one distinct item."""
+    draw out as the test item.  Popular items are drawn repeatedly, so de-duplication loses
+    nonzeros; `calibrate` extra rounds rescale the number of draws until the train matrix holds
+    ~nnz entries."""
+    draws_total = nnz
+    for _ in range(calibrate + 1):
+        out = _powerlaw_csr_once(M, N, draws_total, nnz, sigma, clip, zipf, seed)
+        if abs(out.nnz - nnz) <= 0.01 * nnz:
+            break
+        draws_total = int(draws_total * nnz / max(out.nnz, 1))
+    return out
+
+
+def _powerlaw_csr_once(M, N, draws_total, nnz, sigma, clip, zipf, seed) -> Interactions:
     rng = np.random.default_rng(seed)
-    deg = _degrees(rng, M, nnz, sigma, (clip[0], min(clip[1], N - 1)))
+    deg = _degrees(rng, M, draws_total, sigma, (clip[0], min(clip[1] * max(1, draws_total // nnz), N - 1)))
     cdf, perm = _item_cdf(rng, N, zipf)
     draws = deg + 1
     owner = np.repeat(np.arange(M, dtype=np.int64), draws)
@@ -99,16 +111,29 @@ def powerlaw_csr(M, N, nnz, sigma=1.0, clip=(1, 4000), zipf=0.9, seed=0, **_) ->
 
 
 def powerlaw_csr_device(M, N, nnz, sigma=1.0, clip=(1, 5000), zipf=1.0, seed=0, col_cap=None,
-                        device="cuda", chunk=64_000_000, **_):
+                        device="cuda", chunk=64_000_000, calibrate=2, **_):
     """Device generator (torch tensors on ``device``): returns (row_ptr int64, col_idx int32,
-    test_items int32).  Same scheme as ``powerlaw_csr``; generated in chunks of users so the sort
-    keys stay well inside HBM."""
+    test_items int32).  Same scheme as ``powerlaw_csr`` (incl. the calibration rounds that make up
+    for de-duplication losses); generated in chunks of users so the sort keys stay well inside HBM."""
+    draws_total = nnz
+    for _ in range(calibrate + 1):
+        row_ptr, col_idx, test_items = _powerlaw_csr_device_once(M, N, draws_total, nnz, sigma, clip, zipf, seed,
+                                                                 col_cap, device, chunk)
+        got = int(row_ptr[-1])
+        if abs(got - nnz) <= 0.01 * nnz:
+            break
+        del col_idx
+        draws_total = int(draws_total * nnz / max(got, 1))
+    return row_ptr, col_idx, test_items
+
+
+def _powerlaw_csr_device_once(M, N, draws_total, nnz, sigma, clip, zipf, seed, col_cap, device, chunk):
     import torch
 
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     rng = np.random.default_rng(seed)
-    deg_np = _degrees(rng, M, nnz, sigma, (clip[0], min(clip[1], N - 1)))
+    deg_np = _degrees(rng, M, draws_total, sigma, (clip[0], min(clip[1] * max(1, draws_total // nnz), N - 1)))
     cdf_np, perm_np = _item_cdf(rng, N, zipf, None if col_cap is None else col_cap / max(nnz, 1))
     cdf = torch.from_numpy(cdf_np).to(device)
     perm = torch.from_numpy(perm_np).to(device)

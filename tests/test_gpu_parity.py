@@ -69,8 +69,8 @@ def test_weighted_ratings_match_oracle():
     assert abs(lg - lc) <= 1e-10 * abs(lc)
 
 
-def test_long_rows_use_cta_path():
-    """Rows far longer than a warp tile (CTA kernel) and a dense column."""
+def test_long_rows_use_row_block_path():
+    """Rows of 129..1500 nonzeros (one-CTA blocked kernel and the slab pipeline) and dense columns."""
     M, N, K = 64, 2000, 64
     rng = np.random.default_rng(3)
     row_ptr, cols = [0], []
@@ -85,6 +85,68 @@ def test_long_rows_use_cta_path():
         fals.update_item(); port.update_item()
     assert np.abs(fals.U - port.U).max() < 1e-10
     assert np.abs(fals.V - port.V).max() < 1e-10
+    lg, lc = fals.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc)
+
+
+def _heavy_matrix(M, N, heavy_cols, heavy_len, seed):
+    """A few columns rated by `heavy_len` users each (heavy rows on the item side), sparse rest."""
+    rng = np.random.default_rng(seed)
+    rows = [set() for _ in range(M)]
+    for c in heavy_cols:
+        for u in rng.choice(M, size=heavy_len, replace=False):
+            rows[u].add(int(c))
+    for u in range(M):
+        for c in rng.choice(N, size=int(rng.integers(1, 4)), replace=False):
+            rows[u].add(int(c))
+    row_ptr = np.zeros(M + 1, np.int64)
+    cols = []
+    for u in range(M):
+        c = np.array(sorted(rows[u]), np.int32)
+        cols.append(c)
+        row_ptr[u + 1] = row_ptr[u] + len(c)
+    return row_ptr, np.concatenate(cols)
+
+
+@pytest.mark.parametrize("K", [16, 64])
+def test_heavy_rows_slab_pipeline(K, monkeypatch):
+    """Columns of 1300..5000 nonzeros (> 1024: slab pipeline), several batches, plus one-CTA rows."""
+    monkeypatch.setenv("EALS_HEAVY_BATCH_NNZ", "6000")
+    M, N = 6000, 60
+    row_ptr, col_idx = _heavy_matrix(M, N, heavy_cols=[3, 7, 11, 20, 33], heavy_len=1300, seed=K)
+    row_ptr2, col_idx2 = _heavy_matrix(M, N, heavy_cols=[5], heavy_len=5000, seed=K + 1)
+    # merge the two patterns
+    rows = [sorted(set(col_idx[row_ptr[u]:row_ptr[u + 1]]) | set(col_idx2[row_ptr2[u]:row_ptr2[u + 1]])) for u in range(M)]
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col_idx = np.concatenate([np.array(r, np.int32) for r in rows])
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        assert np.abs(fals.U - port.U).max() < 1e-10
+        fals.update_item(); port.update_item()
+        assert np.abs(fals.V - port.V).max() < 1e-10
+    lg, lc = fals.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc)
+    # single-row API on a heavy row and on a one-CTA row
+    fals.update_item_thread(5); port.update_item(5, 6)
+    fals.update_item_thread(3); port.update_item(3, 4)
+    assert np.abs(fals.V - port.V).max() < 1e-10
+
+
+def test_ultra_heavy_row_two_level_reduction():
+    """One column rated by 270k users: 528 slabs -> the grouped (two-level) partial reduction."""
+    M, N, K = 270_000, 6, 16
+    rng = np.random.default_rng(12)
+    extra = rng.integers(1, N, size=M).astype(np.int32)
+    row_ptr = np.arange(0, 2 * M + 1, 2, dtype=np.int64)
+    col_idx = np.empty(2 * M, np.int32)
+    col_idx[0::2] = 0
+    col_idx[1::2] = extra
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    fals.update_user(); port.update_user()
+    fals.update_item(); port.update_item()
+    assert np.abs(fals.U - port.U).max() < 1e-10
+    assert np.abs(fals.V - port.V).max() < 1e-9
     lg, lc = fals.loss(), port.loss()
     assert abs(lg - lc) <= 1e-10 * abs(lc)
 
