@@ -316,6 +316,7 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     launches = fals.kernel_launches() - launches0
+    detail_ms = fals.timings_detail()
     phase_ms, phase_calls = fals.timings_total(reset=True)
     value = 2.0 * nnz * K / (ms_step * 1e-3)
 
@@ -399,6 +400,7 @@ def main():
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
             "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items() if phase_calls[k]},
+            "sweep_detail_ms_per_step": {k: v / args.steps for k, v in detail_ms.items()},
             "loss_after": loss,
         }
         print(json.dumps(line), flush=True)

@@ -76,6 +76,7 @@ SIGNATURES = {
     "eals_kernel_launches": (C.c_int64, [_P]),
     "eals_timings": (C.c_int, [_P, _P]),
     "eals_timings_total": (C.c_int, [_P, _P, _P, C.c_int32]),
+    "eals_timings_detail": (C.c_int, [_P, _P, _P]),
 }
 
 _lib = None

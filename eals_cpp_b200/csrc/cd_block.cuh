@@ -248,6 +248,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       const double w = a.val ? a.val[p0 + j] : 1.0;
       wr[m] = w * w;
       cw[m] = w - (USER ? a.Wi[id] : wi_row);
+      if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
     }
     if (j < Sm::kRows) c_s[j] = cw[m];
   }
@@ -256,8 +257,8 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
 
   const int nblocks = (K + kFB - 1) / kFB;
 
-  // Pass 1: prediction cache p_j = <x, y_j>
-  for (int fb = 0; fb < nblocks; fb++) {
+  // Pass 1: prediction cache p_j = <x, y_j> (skipped when the symmetric cache is valid)
+  for (int fb = 0; fb < (a.use_cache ? 0 : nblocks); fb++) {
     stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
     cp_async_commit();
     cp_async_wait<0>();
@@ -335,6 +336,13 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
     __syncthreads();
   }
   for (int k = tid; k < K; k += kBlkThreads) xrow[k] = x_s[k];
+  if (a.pcache) {
+#pragma unroll
+    for (int m = 0; m < MW; m++) {
+      const int j = m * kBlkThreads + tid;
+      if (j < n) a.pcache[cache_pos(a, p0 + j)] = pr[m];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -429,7 +437,7 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
       const double w = a.val ? a.val[off + j] : 1.0;
       wr[m] = w * w;
       cw[m] = w - (USER ? a.Wi[id] : wi_row);
-      pr[m] = pred[poff + j];
+      pr[m] = (fb == 0 && a.use_cache) ? a.pcache[cache_pos(a, off + j)] : pred[poff + j];
     }
     c_s[j] = cw[m];
   }
@@ -451,12 +459,20 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
 #pragma unroll
         for (int e = 0; e < 16; e++) acc += delta_s[e] * y[e];
         pr[m] = acc;
-        pred[poff + j] = acc;
+        if (fb < nblocks) pred[poff + j] = acc;
+        else if (a.pcache) a.pcache[cache_pos(a, off + j)] = acc;   // final value -> symmetric cache
       }
     }
     __syncthreads();
   }
   if (fb >= nblocks) return;
+  if (fb == 0 && a.use_cache) {   // the pipeline's compact cache starts from the symmetric one
+#pragma unroll
+    for (int m = 0; m < MW; m++) {
+      const int j = m * kBlkThreads + tid;
+      if (j < n) pred[poff + j] = pr[m];
+    }
+  }
 
   stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
   cp_async_commit();

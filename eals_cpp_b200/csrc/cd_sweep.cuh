@@ -37,7 +37,16 @@ struct CdSide {
   int row_base;         // global id of owned row 0
   int K;
   double reg;
+  // Symmetric prediction cache (single-rank models): pcache[q] = <u, v> of nonzero q in CSR order.
+  // The value a user sweep leaves behind is exactly the one the item sweep starts from (and vice
+  // versa), so the gather pass that rebuilds it (MF_fastALS.cpp:261-270 / 352-363) is skipped.
+  // perm maps this side's nonzero positions to CSR positions (nullptr on the user side).
+  double* pcache;       // nullptr: no cache
+  const uint32_t* perm;
+  int use_cache;        // 1: pcache is valid on entry, read it instead of recomputing
 };
+
+__device__ __forceinline__ int64_t cache_pos(const CdSide& a, int64_t q) { return a.perm ? (int64_t)a.perm[q] : q; }
 
 // ---------------------------------------------------------------------------------------------
 // Warp-per-row kernel: rows with 1..32*MAXM nonzeros.  Lane l owns nonzeros l, l+32, ...; their
@@ -111,6 +120,7 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
       const double w = a.val ? a.val[p0 + j] : 1.0;
       wr[m] = w * w;                                   // w_ui * r_ui, both are the stored value
       cw[m] = w - (USER ? a.Wi[id] : wi_row);
+      if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
     }
   }
   __syncwarp();
@@ -118,7 +128,7 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
   const int nblocks = (K + kFB - 1) / kFB;
 
   // Pass 1: prediction cache  pred_j = <x, y_j>, accumulated in factor order.
-  for (int fb = 0; fb < nblocks; fb++) {
+  for (int fb = 0; fb < (a.use_cache ? 0 : nblocks); fb++) {
     stage_block<LD, MAXM>(tile, idx_s, a.Y, n, fb);
     __syncwarp();
 #pragma unroll
@@ -168,6 +178,11 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
     }
   }
   for (int k = lane; k < K; k += 32) xrow[k] = u_s[k];
+  if (a.pcache) {
+#pragma unroll
+    for (int m = 0; m < MAXM; m++)
+      if (ok[m]) a.pcache[cache_pos(a, p0 + m * 32 + lane)] = pr[m];
+  }
 }
 
 }  // namespace eals

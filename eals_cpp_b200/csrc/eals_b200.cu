@@ -94,7 +94,10 @@ struct Side {
   std::vector<int64_t> h_ptr;         // host copy of ptr (rebased to 0)
 };
 
-enum { T_USER_SWEEP, T_USER_GRAM, T_ITEM_SWEEP, T_ITEM_GRAM, T_LOSS, T_EVAL, T_COUNT };
+enum { T_USER_SWEEP, T_USER_GRAM, T_ITEM_SWEEP, T_ITEM_GRAM, T_LOSS, T_EVAL,
+       // sub-phases of the sweeps (eals_timings_detail): heavy slab pipeline, one-CTA rows, warp rows
+       T_U_HEAVY, T_U_MID, T_U_WARP, T_I_HEAVY, T_I_MID, T_I_WARP, T_COUNT };
+constexpr int kPublicTimers = 6;
 
 }  // namespace
 
@@ -118,6 +121,12 @@ struct eals_model {
   double acc_ms[T_COUNT] = {0};
   int64_t acc_calls[T_COUNT] = {0};
   bool factors_set = false;
+  // symmetric prediction cache (single-rank models only)
+  double* pcache = nullptr;      // [nnz] in CSR order
+  uint32_t* csc2csr = nullptr;   // CSC position -> CSR position
+  bool pcache_valid = false;
+  int sweeps_since_fresh = 0;
+  int pred_refresh_every = 0;    // EALS_PRED_REFRESH_EVERY: recompute the cache from scratch every n sweeps (0 = never)
 };
 
 namespace {
@@ -168,6 +177,58 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ ptr, const int32
 }
 
 int ensure_partials(eals_model* m, size_t n);
+
+// csc2csr[q] = position in the CSR arrays of the nonzero stored at CSC position q.
+__global__ void build_csc2csr_kernel(const int64_t* __restrict__ col_ptr, const int32_t* __restrict__ row_idx, int N,
+                                     const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                     int64_t nnz, uint32_t* __restrict__ perm) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nnz) return;
+  int lo = 0, hi = N;                       // largest i with col_ptr[i] <= q
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (col_ptr[mid] <= q) lo = mid; else hi = mid;
+  }
+  const int i = lo, u = row_idx[q];
+  int64_t a = row_ptr[u], b = row_ptr[u + 1];
+  while (b - a > 1) {
+    const int64_t mid = (a + b) >> 1;
+    if (col_idx[mid] <= i) a = mid; else b = mid;
+  }
+  perm[q] = col_idx[a] == i ? (uint32_t)a : 0xffffffffu;
+}
+
+__global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz, int* __restrict__ bad) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nnz && perm[q] == 0xffffffffu) atomicExch(bad, 1);
+}
+
+// (Re)build the symmetric prediction cache structures after the matrix changed.
+int build_pred_cache(eals_model* m) {
+  cudaFree(m->pcache); cudaFree(m->csc2csr);
+  m->pcache = nullptr; m->csc2csr = nullptr; m->pcache_valid = false;
+  const bool single_rank = m->ub == 0 && m->ue == m->M && m->ib == 0 && m->ie == m->N;
+  const int64_t nnz = m->users.nnz;
+  const char* off = getenv("EALS_NO_PRED_CACHE");
+  if (!single_rank || nnz == 0 || nnz >= 0xffffffffLL || nnz != m->items.nnz || (off && off[0] == '1')) return EALS_OK;
+  OK(dev_alloc(&m->pcache, (size_t)nnz));
+  OK(dev_alloc(&m->csc2csr, (size_t)nnz));
+  const unsigned grid = (unsigned)((nnz + 255) / 256);
+  build_csc2csr_kernel<<<grid, 256, 0, m->stream>>>(m->items.ptr, m->items.idx, m->N, m->users.ptr, m->users.idx, nnz, m->csc2csr);
+  OK(check_launch(m));
+  int* bad;
+  OK(dev_alloc(&bad, 1));
+  CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
+  check_perm_kernel<<<grid, 256, 0, m->stream>>>(m->csc2csr, nnz, bad);
+  OK(check_launch(m));
+  int h_bad = 0;
+  CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  cudaFree(bad);
+  if (h_bad) return fail(EALS_ERR_ARG, "the CSR and CSC arrays do not describe the same matrix");
+  if (const char* e = getenv("EALS_PRED_REFRESH_EVERY")) m->pred_refresh_every = atoi(e);
+  return EALS_OK;
+}
 
 // Upload the owned slice [begin, end) of one orientation of the matrix and bucket its rows.
 int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int space,
@@ -430,9 +491,17 @@ int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b
   double* part2 = m->partials + (size_t)nu * eals::kPartLen;
   auto step = eals::heavy_step_kernel<LD, USER>;
   CU(cudaFuncSetAttribute(step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eals::HeavySmem::kBytes));
-  eals::heavy_pred_kernel<LD><<<nu, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.u0, s.pred);
-  OK(check_launch(m));
-  for (int fb = 0; fb < nblocks; fb++) {
+  if (!a.use_cache) {
+    eals::heavy_pred_kernel<LD><<<nu, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.u0, s.pred);
+    OK(check_launch(m));
+  }
+  for (int fb = 0; fb <= nblocks; fb++) {
+    if (fb == nblocks) {   // last cache update; only needed when the symmetric cache keeps the result
+      if (!a.pcache) break;
+      step<<<nu, eals::kBlkThreads, eals::HeavySmem::kBytes, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
+      OK(check_launch(m));
+      break;
+    }
     step<<<nu, eals::kBlkThreads, eals::HeavySmem::kBytes, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
     OK(check_launch(m));
     if (two_level) {
@@ -467,13 +536,20 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     return launch_cd_row_block<LD, 4, USER>(m, a, one, 0, 1);
   }
   // heavy rows first: their launch chain is the longest
+  const int t0 = USER ? T_U_HEAVY : T_I_HEAVY;
+  tic(m, t0);
   for (const HeavyBatch& b : s.batches) OK((run_heavy_batch<LD, USER>(m, s, a, b)));
+  toc(m, t0);
+  tic(m, t0 + 1);
   OK((launch_cd_row_block<LD, 4, USER>(m, a, s.order, s.first[6], s.first[7] - s.first[6])));
   OK((launch_cd_row_block<LD, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));
   OK((launch_cd_row_block<LD, 1, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
+  toc(m, t0 + 1);
+  tic(m, t0 + 2);
   OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
   OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
   OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
+  toc(m, t0 + 2);
   return EALS_OK;
 }
 
@@ -489,6 +565,17 @@ int sweep(eals_model* m, bool user, int only_row) {
   a.row_base = s.row_base;
   a.K = m->K;
   a.reg = m->p.reg;
+  a.pcache = nullptr; a.perm = nullptr; a.use_cache = 0;
+  if (only_row >= 0) {
+    m->pcache_valid = false;           // a single-row update changes factors behind the cache's back
+  } else if (m->pcache) {
+    if (m->pred_refresh_every > 0 && m->sweeps_since_fresh >= m->pred_refresh_every) m->pcache_valid = false;
+    a.pcache = m->pcache;
+    a.perm = user ? nullptr : m->csc2csr;
+    a.use_cache = m->pcache_valid ? 1 : 0;
+    m->sweeps_since_fresh = m->pcache_valid ? m->sweeps_since_fresh + 1 : 0;
+    m->pcache_valid = true;            // every nonzero's final prediction is stored by this sweep
+  }
   if (user) { DISPATCH_LD(m->LD, OK((launch_cd<LD, true>(m, s, a, only_row)))); }
   else      { DISPATCH_LD(m->LD, OK((launch_cd<LD, false>(m, s, a, only_row)))); }
   return sync_if_debug(m);
@@ -779,7 +866,7 @@ int eals_destroy(eals_model* m) {
   free_side(m->users);
   free_side(m->items);
   cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
-  cudaFree(m->terms); cudaFree(m->partials);
+  cudaFree(m->terms); cudaFree(m->partials); cudaFree(m->pcache); cudaFree(m->csc2csr);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -839,6 +926,7 @@ int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t
   TRY(build_side(m, m->users, m->ub, m->ue, m->N, params->input_space, row_ptr, col_idx, row_val));
   TRY(build_side(m, m->items, m->ib, m->ie, m->M, params->input_space, col_ptr, row_idx, col_val));
   TRY(compute_item_weights(m, params->input_space, col_ptr));
+  TRY(build_pred_cache(m));
   TRYCU(cudaStreamSynchronize(m->stream));
 #undef TRY
 #undef TRYCU
@@ -854,7 +942,7 @@ int eals_set_train(eals_model* m, int32_t input_space, const int64_t* row_ptr, c
   CU(cudaSetDevice(m->p.device));
   OK(build_side(m, m->users, m->ub, m->ue, m->N, input_space, row_ptr, col_idx, row_val));
   OK(build_side(m, m->items, m->ib, m->ie, m->M, input_space, col_ptr, row_idx, col_val));
-  return EALS_OK;
+  return build_pred_cache(m);
 }
 
 int eals_refresh_S(eals_model* m) {
@@ -884,6 +972,7 @@ int eals_init_factors(eals_model* m) {
   OK(upload_dense(m, m->V, stream.data(), (size_t)m->N, EALS_HOST));
   CU(cudaStreamSynchronize(m->stream));
   m->factors_set = true;
+  m->pcache_valid = false;
   return eals_refresh_S(m);
 }
 
@@ -894,6 +983,7 @@ int eals_set_factors(eals_model* m, int32_t space, const double* U, const double
   if (V) OK(upload_dense(m, m->V, V, (size_t)m->N, space));
   CU(cudaStreamSynchronize(m->stream));
   m->factors_set = true;
+  m->pcache_valid = false;
   return eals_refresh_S(m);
 }
 
@@ -1070,8 +1160,9 @@ int eals_device_buffer(eals_model* m, int32_t which, void** dev_ptr, int64_t* by
   void* p = nullptr;
   int64_t b = 0;
   switch (which) {
-    case EALS_BUF_U: p = m->U; b = (int64_t)m->M * m->LD * 8; break;
-    case EALS_BUF_V: p = m->V; b = (int64_t)m->N * m->LD * 8; break;
+    // handing out U or V lets the caller change factors behind the prediction cache's back
+    case EALS_BUF_U: p = m->U; b = (int64_t)m->M * m->LD * 8; m->pcache_valid = false; break;
+    case EALS_BUF_V: p = m->V; b = (int64_t)m->N * m->LD * 8; m->pcache_valid = false; break;
     case EALS_BUF_SU: p = m->SU; b = (int64_t)m->K * m->LD * 8; break;
     case EALS_BUF_SV: p = m->SV; b = (int64_t)m->K * m->LD * 8; break;
     case EALS_BUF_WI: p = m->Wi; b = (int64_t)m->N * 8; break;
@@ -1114,7 +1205,7 @@ int eals_timings(eals_model* m, double ms[6]) {
   CU(cudaSetDevice(m->p.device));
   CU(cudaStreamSynchronize(m->stream));
   fold_timings(m);
-  for (int t = 0; t < T_COUNT; t++) ms[t] = m->last_ms[t];
+  for (int t = 0; t < kPublicTimers; t++) ms[t] = m->last_ms[t];
   return EALS_OK;
 }
 
@@ -1123,10 +1214,22 @@ int eals_timings_total(eals_model* m, double ms[6], int64_t calls[6], int32_t re
   CU(cudaSetDevice(m->p.device));
   CU(cudaStreamSynchronize(m->stream));
   fold_timings(m);
-  for (int t = 0; t < T_COUNT; t++) {
+  for (int t = 0; t < kPublicTimers; t++) {
     if (ms) ms[t] = m->acc_ms[t];
     if (calls) calls[t] = m->acc_calls[t];
-    if (reset) { m->acc_ms[t] = 0; m->acc_calls[t] = 0; }
+  }
+  if (reset) for (int t = 0; t < T_COUNT; t++) { m->acc_ms[t] = 0; m->acc_calls[t] = 0; }
+  return EALS_OK;
+}
+
+int eals_timings_detail(eals_model* m, double ms[6], int64_t calls[6]) {
+  if (!m || !ms) return fail(EALS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaStreamSynchronize(m->stream));
+  fold_timings(m);
+  for (int t = 0; t < 6; t++) {
+    ms[t] = m->acc_ms[T_U_HEAVY + t];
+    if (calls) calls[t] = m->acc_calls[T_U_HEAVY + t];
   }
   return EALS_OK;
 }

@@ -281,6 +281,10 @@ class MF_fastALS:
             space = _lib.EALS_DEVICE
         check(self.lib.eals_set_factors(self.h, space, _ptr(U), _ptr(V)))
 
+    def refresh_S(self):
+        """initS (MF_fastALS.cpp:583-595): rebuild both S caches from the current factors."""
+        check(self.lib.eals_refresh_S(self.h))
+
     def setTrain(self, trainMatrix: SparseMat):
         sm = trainMatrix
         space = _lib.EALS_DEVICE if sm.on_device else _lib.EALS_HOST
@@ -416,6 +420,13 @@ class MF_fastALS:
         ms, calls = np.zeros(6), np.zeros(6, np.int64)
         check(self.lib.eals_timings_total(self.h, _ptr(ms), _ptr(calls), int(reset)))
         return dict(zip(self.PHASES, ms.tolist())), dict(zip(self.PHASES, calls.tolist()))
+
+    def timings_detail(self):
+        """Accumulated device ms of the sweep sub-phases (heavy / one-CTA / warp rows per side)."""
+        ms, calls = np.zeros(6), np.zeros(6, np.int64)
+        check(self.lib.eals_timings_detail(self.h, _ptr(ms), _ptr(calls)))
+        names = ("user_heavy", "user_mid", "user_warp", "item_heavy", "item_mid", "item_warp")
+        return dict(zip(names, ms.tolist()))
 
     def kernel_launches(self) -> int:
         return int(self.lib.eals_kernel_launches(self.h))

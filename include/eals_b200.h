@@ -190,6 +190,10 @@ int eals_timings(eals_model* m, double ms[6]);
 /* Device milliseconds and call counts of every call since the last reset, same six slots; each call
  * is bracketed by CUDA events on the model's stream, nothing synchronises until this query. */
 int eals_timings_total(eals_model* m, double ms[6], int64_t calls[6], int32_t reset);
+/* Accumulated device milliseconds of the sweep sub-phases since the last reset of
+ * eals_timings_total: [0..2] user side heavy-row slab pipeline / one-CTA rows / warp rows,
+ * [3..5] the same for the item side.  Query BEFORE eals_timings_total(reset=1). */
+int eals_timings_detail(eals_model* m, double ms[6], int64_t calls[6]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,56 @@
+"""Worker for the multi-GPU parity test: run under torch.distributed.run with N ranks (one per GPU).
+Every rank builds the same small matrix, trains 3 epochs with users/items sharded over the ranks and
+checks its replica of U, V, the loss and the evaluation against the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from conftest import random_csr
+    from eals_cpp_b200.model import MF_fastALS, SparseMat
+    from oracle.bindings import PortModel
+    M, N, K = 1500, 700, 32
+    row_ptr, col_idx = random_csr(M, N, 20, seed=42, empty_frac=0.03)
+    # a few heavy columns so that every kernel family runs on some rank
+    rng = np.random.default_rng(1)
+    rows = [set(col_idx[row_ptr[u]:row_ptr[u + 1]].tolist()) for u in range(M)]
+    for c in (3, 250, 600):
+        for u in rng.choice(M, size=1200, replace=False):
+            rows[u].add(c)
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col_idx = np.concatenate([np.array(sorted(r), np.int32) for r in rows])
+    gt = np.random.default_rng(2).integers(0, N, M).astype(np.int32)
+    sm = SparseMat.from_csr(M, N, row_ptr, col_idx)
+    fals = MF_fastALS(sm, gt, factors=K, showLoss=False, device=local)
+    assert fals.world == dist.get_world_size() and fals.world > 1
+    port = PortModel(M, N, row_ptr, col_idx, factors=K)
+    for it in range(3):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+        lg, lc = fals.loss(), port.loss()
+        assert abs(lg - lc) <= 1e-10 * abs(lc), (rank, it, lg, lc)
+    assert np.abs(fals.U - port.U).max() < 1e-10, rank        # every replica is complete
+    assert np.abs(fals.V - port.V).max() < 1e-10, rank
+    assert np.abs(fals.SU - port.SU).max() <= 1e-11 * np.abs(port.SU).max()
+    res = fals.evaluate()
+    want = port.evaluate(gt, 10, compat=True)[0]
+    assert np.allclose(res, want, rtol=0, atol=1e-12), (res, want)
+    dist.barrier()
+    if rank == 0:
+        print(f"dist parity ok: world {fals.world}, loss {lg!r}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,25 @@ def _models(M, N, row_ptr, col_idx, K, val=None, **kw):
     return fals, port
 
 
+def _heavy_matrix(M, N, heavy_cols, heavy_len, seed):
+    """A few columns rated by `heavy_len` users each (heavy rows on the item side), sparse rest."""
+    rng = np.random.default_rng(seed)
+    rows = [set() for _ in range(M)]
+    for c in heavy_cols:
+        for u in rng.choice(M, size=heavy_len, replace=False):
+            rows[u].add(int(c))
+    for u in range(M):
+        for c in rng.choice(N, size=int(rng.integers(1, 4)), replace=False):
+            rows[u].add(int(c))
+    row_ptr = np.zeros(M + 1, np.int64)
+    cols = []
+    for u in range(M):
+        c = np.array(sorted(rows[u]), np.int32)
+        cols.append(c)
+        row_ptr[u + 1] = row_ptr[u] + len(c)
+    return row_ptr, np.concatenate(cols)
+
+
 @pytest.mark.parametrize("K", [8, 16, 64, 128, 20])
 def test_init_and_S_match_oracle(K):
     row_ptr, col_idx = random_csr(300, 200, 12, seed=K)
@@ -52,6 +71,45 @@ def test_half_epochs_and_loss_match_oracle(K, shape):
         assert abs(lg - lc) <= 1e-10 * abs(lc), (it, lg, lc)
     assert np.abs(fals.SU - port.SU).max() <= 1e-11 * np.abs(port.SU).max()
     assert np.abs(fals.SV - port.SV).max() <= 1e-11 * np.abs(port.SV).max()
+
+
+@pytest.mark.parametrize("mode", ["cache", "nocache", "refresh2"])
+def test_prediction_cache_modes_agree_with_oracle(mode, monkeypatch):
+    """The symmetric prediction cache (default on one GPU), the recompute-every-sweep path that
+    multi-rank models use, and periodic refresh all track the oracle over several epochs, across
+    all three kernel families (warp rows, one-CTA rows, slab pipeline)."""
+    if mode == "nocache":
+        monkeypatch.setenv("EALS_NO_PRED_CACHE", "1")
+    if mode == "refresh2":
+        monkeypatch.setenv("EALS_PRED_REFRESH_EVERY", "2")
+    M, N, K = 2500, 80, 32
+    row_ptr, col_idx = _heavy_matrix(M, N, heavy_cols=[1, 9], heavy_len=1800, seed=3)
+    row_ptr2, col_idx2 = _heavy_matrix(M, N, heavy_cols=[4, 5, 6], heavy_len=300, seed=4)
+    rows = [sorted(set(col_idx[row_ptr[u]:row_ptr[u + 1]]) | set(col_idx2[row_ptr2[u]:row_ptr2[u + 1]])) for u in range(M)]
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col_idx = np.concatenate([np.array(r, np.int32) for r in rows])
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for it in range(5):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+        assert np.abs(fals.U - port.U).max() < 1e-10, it
+        assert np.abs(fals.V - port.V).max() < 1e-10, it
+        lg, lc = fals.loss(), port.loss()
+        assert abs(lg - lc) <= 1e-10 * abs(lc)
+    # factors replaced from outside: the cache must be dropped, not reused
+    U, V = port.U * 0.5, port.V * 2.0
+    port.U[:], port.V[:] = U, V
+    port.init_S()
+    fals.setUV(U, V)
+    fals.update_user(); port.update_user()
+    fals.update_item(); port.update_item()
+    assert np.abs(fals.U - port.U).max() < 1e-10
+    assert np.abs(fals.V - port.V).max() < 1e-10
+    # single-row updates also invalidate it
+    fals.update_user_thread(3); port.update_user(3, 4)
+    fals.refresh_S(); port.init_S()
+    fals.update_item(); port.update_item()
+    assert np.abs(fals.V - port.V).max() < 1e-10
 
 
 def test_weighted_ratings_match_oracle():
@@ -87,25 +145,6 @@ def test_long_rows_use_row_block_path():
     assert np.abs(fals.V - port.V).max() < 1e-10
     lg, lc = fals.loss(), port.loss()
     assert abs(lg - lc) <= 1e-10 * abs(lc)
-
-
-def _heavy_matrix(M, N, heavy_cols, heavy_len, seed):
-    """A few columns rated by `heavy_len` users each (heavy rows on the item side), sparse rest."""
-    rng = np.random.default_rng(seed)
-    rows = [set() for _ in range(M)]
-    for c in heavy_cols:
-        for u in rng.choice(M, size=heavy_len, replace=False):
-            rows[u].add(int(c))
-    for u in range(M):
-        for c in rng.choice(N, size=int(rng.integers(1, 4)), replace=False):
-            rows[u].add(int(c))
-    row_ptr = np.zeros(M + 1, np.int64)
-    cols = []
-    for u in range(M):
-        c = np.array(sorted(rows[u]), np.int32)
-        cols.append(c)
-        row_ptr[u + 1] = row_ptr[u] + len(c)
-    return row_ptr, np.concatenate(cols)
 
 
 @pytest.mark.parametrize("K", [16, 64])
