@@ -153,38 +153,40 @@ __device__ __forceinline__ void scatter_partial(int i, double v, double* Gs, dou
 }
 
 // The per-row, per-block solve, by ONE warp.  x_s: the row's K factors (shared, updated in place);
-// Gs/Pt: summed Gram and right-hand side of the block; delta_s[16] receives d_f.
+// Gs: summed local Gram of the block; pp[f]: this lane's contribution to P_f (the warp total is
+// what counts: callers holding the total pass it in lane 0 and zeros elsewhere); delta_s[16]
+// receives d_f.  One reciprocal per factor (all 16 in parallel) replaces the reference's divide.
 template <int LD>
-__device__ __forceinline__ void solve_block(double* x_s, const double* Gs, const double* Pt, double* delta_s,
+__device__ __forceinline__ void solve_block(double* x_s, const double* Gs, double (&pp)[16], double* delta_s,
                                             const double* __restrict__ S, int f0, int K, double g, double reg) {
   const int lane = lane_id();
   // t_f = sum_k x_k S[f0+f][k], k split over lanes; folded with P into base_f = P_f - g t_f
-  double bp[16];
+  double tp[16];
 #pragma unroll
-  for (int f = 0; f < 16; f++) bp[f] = 0.0;
+  for (int f = 0; f < 16; f++) tp[f] = 0.0;
   for (int k = lane; k < K; k += 32) {
     const double xk = x_s[k];
+    const double* __restrict__ Sk = S + (size_t)f0 * LD + k;
 #pragma unroll
-    for (int f = 0; f < 16; f++) bp[f] += xk * __ldg(S + (size_t)(f0 + f) * LD + k);
+    for (int f = 0; f < 16; f++) tp[f] += xk * __ldg(Sk + (size_t)f * LD);
   }
 #pragma unroll
-  for (int f = 0; f < 16; f++) bp[f] = (lane == 0 ? Pt[f] : 0.0) - g * bp[f];
-  const double base_pair = warp_reduce16(bp);                       // lanes 2f, 2f+1 hold base_f
+  for (int f = 0; f < 16; f++) pp[f] -= g * tp[f];
+  const double base_pair = warp_reduce16(pp);                       // lanes 2f, 2f+1 hold base_f
   const int f = lane & 15;
   const double base = __shfl_sync(kFullMask, base_pair, 2 * f);
   double h[16];
+  const double* __restrict__ Sb = S + (size_t)f0 * LD + f0 + f;
 #pragma unroll
-  for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + f] + g * __ldg(S + (size_t)(f0 + k) * LD + f0 + f);
+  for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + f] + g * __ldg(Sb + (size_t)k * LD);
   const double xf = x_s[f0 + f];
-  double hff = 0.0;
-#pragma unroll
-  for (int k = 0; k < 16; k++) hff = (k == f) ? h[k] : hff;
+  const double hff = Gs[f * 16 + f] + g * __ldg(Sb + (size_t)f * LD);
   double numer = base + xf * hff;
-  const double denom = hff + reg;
+  const double rden = 1.0 / (hff + reg);
   double xnew = xf, mydelta = 0.0;
 #pragma unroll
   for (int s = 0; s < 16; s++) {
-    const double cand = numer / denom;
+    const double cand = numer * rden;
     const double d = cand - xf;
     const double ds = __shfl_sync(kFullMask, d, s);
     if (f == s) { xnew = cand; mydelta = d; }
@@ -193,6 +195,158 @@ __device__ __forceinline__ void solve_block(double* x_s, const double* Gs, const
   if (lane < 16) {
     if (f0 + f < K) x_s[f0 + f] = xnew;
     delta_s[f] = (f0 + f < K) ? mydelta : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One WARP per row, 1 .. 32*MAXM nonzeros (lane l owns nonzeros l, l+32, ...).  Same blocked update
+// as the kernels below; all synchronisation is __syncwarp.  Per 16 factors: one tile of whole
+// 128-byte lines (cp.async, prefetched one block ahead when NBUF = 2), 3 tensor-core tiles per
+// 4 nonzeros, ONE 16-value warp reduction and ONE reciprocal per factor — against one divide and
+// one reduction per factor in the plain sequential form.
+// ---------------------------------------------------------------------------------------------
+template <int LD, int MAXM, int NBUF>
+struct WarpBlockSmem {
+  static constexpr int kRows = 32 * MAXM;
+  static constexpr size_t kTile = (size_t)kRows * 128;
+  static constexpr size_t kBytesPerWarp = NBUF * kTile + (size_t)kRows * 4 + (size_t)kRows * 8 + (size_t)LD * 8 +
+                                          (256 + 16) * 8;
+};
+
+template <int LD, int MAXM, int NBUF, bool USER>
+__global__ void __launch_bounds__(256, 2)
+cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using Sm = WarpBlockSmem<LD, MAXM, NBUF>;
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (slot >= count) return;   // warp-uniform; no block-wide barrier below
+
+  unsigned char* base = smem + (size_t)warp * Sm::kBytesPerWarp;
+  unsigned char* tile0 = base;
+  int* idx_s = reinterpret_cast<int*>(base + NBUF * Sm::kTile);
+  double* c_s = reinterpret_cast<double*>(base + NBUF * Sm::kTile + (size_t)Sm::kRows * 4);
+  double* x_s = c_s + Sm::kRows;
+  double* Gs = x_s + LD;
+  double* delta_s = Gs + 256;
+
+  const int row = order[first + slot];
+  const int64_t p0 = a.ptr[row];
+  const int n = (int)(a.ptr[row + 1] - p0);
+  const int n_pad = (n + 3) & ~3;
+  const int grow = a.row_base + row;
+  double* xrow = a.X + (size_t)grow * LD;
+  const int K = a.K;
+  const double wi_row = USER ? 0.0 : a.Wi[grow];
+  const double g = USER ? 1.0 : wi_row;
+
+  double pr[MAXM], cw[MAXM], wr[MAXM];
+#pragma unroll
+  for (int m = 0; m < MAXM; m++) {
+    const int j = m * 32 + lane;
+    pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
+    if (j < n) {
+      const int id = a.idx[p0 + j];
+      idx_s[j] = id;
+      const double w = a.val ? a.val[p0 + j] : 1.0;
+      wr[m] = w * w;
+      cw[m] = w - (USER ? a.Wi[id] : wi_row);
+      if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
+    }
+    c_s[j] = cw[m];
+  }
+  for (int k = lane; k < LD; k += 32) x_s[k] = xrow[k];
+  __syncwarp();
+
+  const int nblocks = (K + kFB - 1) / kFB;
+
+  if (!a.use_cache) {   // prediction cache from scratch: p_j = <x, y_j>
+    for (int fb = 0; fb < nblocks; fb++) {
+      stage_tile_async<LD>(tile0, idx_s, a.Y, n, n_pad, fb, lane, 32);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < MAXM; m++) {
+        const int j = m * 32 + lane;
+        if (j < n) {
+          double y[16];
+          load_tile_row(tile0, j, y);
+          double acc = pr[m];
+#pragma unroll
+          for (int e = 0; e < 16; e++) acc += x_s[fb * kFB + e] * y[e];
+          pr[m] = acc;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  stage_tile_async<LD>(tile0, idx_s, a.Y, n, n_pad, 0, lane, 32);
+  cp_async_commit();
+  for (int fb = 0; fb < nblocks; fb++) {
+    unsigned char* tile = tile0 + (NBUF == 2 ? (size_t)(fb & 1) * Sm::kTile : 0);
+    if (NBUF == 2 && fb + 1 < nblocks) {
+      stage_tile_async<LD>(tile0 + (size_t)((fb + 1) & 1) * Sm::kTile, idx_s, a.Y, n, n_pad, fb + 1, lane, 32);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+
+    double pp[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) pp[e] = 0.0;
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+      const int j = m * 32 + lane;
+      if (j < n) {
+        double y[16];
+        load_tile_row(tile, j, y);
+        const double z = wr[m] - cw[m] * pr[m];
+#pragma unroll
+        for (int e = 0; e < 16; e++) pp[e] += z * y[e];
+      }
+    }
+    double frag[6] = {0, 0, 0, 0, 0, 0};
+    gram_fragments(tile, c_s, 0, n_pad, frag);
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      scatter_partial(t * 64 + lane * 2, frag[2 * t], Gs, delta_s);
+      scatter_partial(t * 64 + lane * 2 + 1, frag[2 * t + 1], Gs, delta_s);
+    }
+    __syncwarp();
+    solve_block<LD>(x_s, Gs, pp, delta_s, a.S, fb * kFB, K, g, a.reg);
+    __syncwarp();
+    double d[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) d[e] = delta_s[e];
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+      const int j = m * 32 + lane;
+      if (j < n) {
+        double acc = pr[m];
+        double y[16];
+        load_tile_row(tile, j, y);
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc += d[e] * y[e];
+        pr[m] = acc;
+      }
+    }
+    __syncwarp();
+    if (NBUF == 1 && fb + 1 < nblocks) {
+      stage_tile_async<LD>(tile0, idx_s, a.Y, n, n_pad, fb + 1, lane, 32);
+      cp_async_commit();
+    }
+  }
+  for (int k = lane; k < K; k += 32) xrow[k] = x_s[k];
+  if (a.pcache) {
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+      const int j = m * 32 + lane;
+      if (j < n) a.pcache[cache_pos(a, p0 + j)] = pr[m];
+    }
   }
 }
 
@@ -319,7 +473,12 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       scatter_partial(tid, s, Gs, Pt);
     }
     __syncthreads();
-    if (warp == 0) solve_block<LD>(x_s, Gs, Pt, delta_s, a.S, fb * kFB, K, g, a.reg);
+    if (warp == 0) {
+      double pt[16];
+#pragma unroll
+      for (int e = 0; e < 16; e++) pt[e] = lane == 0 ? Pt[e] : 0.0;
+      solve_block<LD>(x_s, Gs, pt, delta_s, a.S, fb * kFB, K, g, a.reg);
+    }
     __syncthreads();
 #pragma unroll
     for (int m = 0; m < MW; m++) {
@@ -567,7 +726,10 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int u0, int fb, const double
   __syncthreads();
   if (tid < 32) {
     const double g = USER ? 1.0 : a.Wi[grow];
-    solve_block<LD>(x_s, Gs, Pt, delta_s, a.S, fb * kFB, a.K, g, a.reg);
+    double pt[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) pt[e] = tid == 0 ? Pt[e] : 0.0;
+    solve_block<LD>(x_s, Gs, pt, delta_s, a.S, fb * kFB, a.K, g, a.reg);
   }
   __syncthreads();
   if (tid < 16) {

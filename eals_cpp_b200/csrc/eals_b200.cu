@@ -66,8 +66,9 @@ constexpr int kNumBuckets = 8;
 constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 128, 256, 512, 1024, 0x7fffffff};
 constexpr int kMidBucket = 4;     // first one-CTA-per-row bucket
 constexpr int kHeavyBucket = 7;
-constexpr int64_t kDefaultBatchNnz = 384 * 1024;   // heavy rows per launch group: one factor block of the
-                                                   // batch (nnz * 128 B = 48 MB) stays L2-resident
+// Heavy rows per launch group.  Measured on c4 (profiles/README.md r01b): launch granularity matters
+// more than keeping one factor block of the batch L2-resident (384k nnz: 363 ms, 24M nnz: 204 ms).
+constexpr int64_t kDefaultBatchNnz = 24 * 1024 * 1024;
 
 struct HeavyBatch { int h0, h1, u0, u1; };
 
@@ -458,6 +459,22 @@ int launch_cd_warp(eals_model* m, const CdSide& a, const int32_t* order, int fir
   return check_launch(m);
 }
 
+template <int LD, int MAXM, bool USER>
+int launch_cd_warp_block(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
+  if (count <= 0) return EALS_OK;
+  constexpr int NBUF = MAXM <= 2 ? 2 : 1;
+  using Sm = eals::WarpBlockSmem<LD, MAXM, NBUF>;
+  // as many warps per CTA as fit ~100 KB, so that two CTAs share an SM
+  int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (100 * 1024) / Sm::kBytesPerWarp));
+  static int env_wpb = getenv("EALS_WARP_WPB") ? atoi(getenv("EALS_WARP_WPB")) : 0;
+  if (env_wpb > 0) wpb = std::min(env_wpb, 8);
+  const size_t smem = Sm::kBytesPerWarp * wpb;
+  auto kern = eals::cd_warp_block_kernel<LD, MAXM, NBUF, USER>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(count + wpb - 1) / wpb, wpb * 32, smem, m->stream>>>(a, order, first, count);
+  return check_launch(m);
+}
+
 template <int LD, int MW, bool USER>
 int launch_cd_row_block(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
   if (count <= 0) return EALS_OK;
@@ -528,9 +545,9 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     OK(ensure_partials(m, 16));
     int32_t* one = reinterpret_cast<int32_t*>(m->partials);
     CU(cudaMemcpyAsync(one, &only_row, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
-    if (n <= 32) return launch_cd_warp<LD, 1, USER>(m, a, one, 0, 1);
-    if (n <= 64) return launch_cd_warp<LD, 2, USER>(m, a, one, 0, 1);
-    if (n <= 128) return launch_cd_warp<LD, 4, USER>(m, a, one, 0, 1);
+    if (n <= 32) return launch_cd_warp_block<LD, 1, USER>(m, a, one, 0, 1);
+    if (n <= 64) return launch_cd_warp_block<LD, 2, USER>(m, a, one, 0, 1);
+    if (n <= 128) return launch_cd_warp_block<LD, 4, USER>(m, a, one, 0, 1);
     if (n <= 256) return launch_cd_row_block<LD, 1, USER>(m, a, one, 0, 1);
     if (n <= 512) return launch_cd_row_block<LD, 2, USER>(m, a, one, 0, 1);
     return launch_cd_row_block<LD, 4, USER>(m, a, one, 0, 1);
@@ -546,9 +563,16 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   OK((launch_cd_row_block<LD, 1, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
   toc(m, t0 + 1);
   tic(m, t0 + 2);
-  OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
-  OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
-  OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
+  static const bool seq = getenv("EALS_WARP_SEQ") && getenv("EALS_WARP_SEQ")[0] == '1';
+  if (seq) {   // the plain sequential form (one reduction + one divide per factor), kept for comparison
+    OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+    OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+    OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
+  } else {
+    OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+    OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+    OK((launch_cd_warp_block<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
+  }
   toc(m, t0 + 2);
   return EALS_OK;
 }
