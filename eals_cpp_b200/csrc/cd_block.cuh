@@ -199,154 +199,245 @@ __device__ __forceinline__ void solve_block(double* x_s, const double* Gs, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// One WARP per row, 1 .. 32*MAXM nonzeros (lane l owns nonzeros l, l+32, ...).  Same blocked update
-// as the kernels below; all synchronisation is __syncwarp.  Per 16 factors: one tile of whole
-// 128-byte lines (cp.async, prefetched one block ahead when NBUF = 2), 3 tensor-core tiles per
-// 4 nonzeros, ONE 16-value warp reduction and ONE reciprocal per factor — against one divide and
-// one reduction per factor in the plain sequential form.
+// One WARP per row, 1 .. 32*MAXM nonzeros (lane l owns nonzeros l, l+32, ...), PERSISTENT CTAs.
+//
+// Measured on the first blocked version (profiles/README.md r01c): 39 % of the stall samples sat on
+// the S-cache loads of the per-block solve (K x K fp64 = 128 KB at K = 128 does not stay in L1) and
+// 9 % of the instructions were the selects of the 16-value shuffle reduction.  Hence:
+//   * the whole S cache is copied to shared memory ONCE per CTA (LD <= 128; CTAs are persistent and
+//     stride over the rows), every S access of the solve is an LDS;
+//   * the right-hand side P_f = sum_j z_j y_jf rides on the tensor cores as two more 8 x 8 tiles (z in
+//     column 0 of the B operand) — no cross-lane reduction at all;
+//   * S.x is split over FACTOR lanes (lane = (f, half of k); S is symmetric, so the lane walks a
+//     column of S with unit stride across lanes) — one shuffle instead of a 16-value butterfly;
+//   * the 16-step in-block Gauss-Seidel is multiply/shuffle/fma only (one reciprocal per factor,
+//     taken in parallel before the loop).
 // ---------------------------------------------------------------------------------------------
-template <int LD, int MAXM, int NBUF>
+template <int LD, int MAXM>
 struct WarpBlockSmem {
+  static constexpr bool kSInSmem = LD <= 128;
   static constexpr int kRows = 32 * MAXM;
+  static constexpr size_t kS = kSInSmem ? (size_t)LD * LD * 8 : 0;
   static constexpr size_t kTile = (size_t)kRows * 128;
-  static constexpr size_t kBytesPerWarp = NBUF * kTile + (size_t)kRows * 4 + (size_t)kRows * 8 + (size_t)LD * 8 +
-                                          (256 + 16) * 8;
+  // tile | idx | c | z | x | Gs[256] | Pt[16] | delta[16]
+  static constexpr size_t kBytesPerWarp = kTile + (size_t)kRows * (4 + 8 + 8) + (size_t)LD * 8 + (256 + 16 + 16) * 8;
 };
 
-template <int LD, int MAXM, int NBUF, bool USER>
-__global__ void __launch_bounds__(256, 2)
+// Gram + right-hand-side fragments of tile rows [0, r1): frag[0..5] as gram_fragments, frag[6..7] =
+// P rows 0..7, frag[8..9] = P rows 8..15 (column 0 of each tile holds the sums).
+__device__ __forceinline__ void gram_rhs_fragments(const unsigned char* tile, const double* c_s, const double* z_s,
+                                                   int r1, double (&frag)[10]) {
+  const int lane = lane_id();
+  const int rr = lane & 3, e0 = lane >> 2;
+  const uint32_t off_lo = (uint32_t)(rr * 128 + ((e0 & 1) << 3));
+  for (int j0 = 0; j0 < r1; j0 += 4) {
+    const int r = j0 + rr;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const unsigned char* rowp = tile + (size_t)j0 * 128 + off_lo;
+    const double a0 = *reinterpret_cast<const double*>(rowp + ((((uint32_t)(e0 >> 1)) ^ sw) << 4));
+    const double a1 = *reinterpret_cast<const double*>(rowp + ((((uint32_t)(4 + (e0 >> 1))) ^ sw) << 4));
+    const double cj = c_s[r];
+    const double zj = e0 == 0 ? z_s[r] : 0.0;
+    const double b0 = cj * a0, b1 = cj * a1;
+    dmma_884(frag[0], frag[1], a0, b0);
+    dmma_884(frag[2], frag[3], a1, b0);
+    dmma_884(frag[4], frag[5], a1, b1);
+    dmma_884(frag[6], frag[7], a0, zj);
+    dmma_884(frag[8], frag[9], a1, zj);
+  }
+}
+
+template <int LD, int MAXM, bool USER>
+__global__ void __launch_bounds__(384, 1)
 cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count) {
   extern __shared__ __align__(128) unsigned char smem[];
-  using Sm = WarpBlockSmem<LD, MAXM, NBUF>;
+  using Sm = WarpBlockSmem<LD, MAXM>;
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (slot >= count) return;   // warp-uniform; no block-wide barrier below
+  const int wpb = blockDim.x >> 5;
 
-  unsigned char* base = smem + (size_t)warp * Sm::kBytesPerWarp;
-  unsigned char* tile0 = base;
-  int* idx_s = reinterpret_cast<int*>(base + NBUF * Sm::kTile);
-  double* c_s = reinterpret_cast<double*>(base + NBUF * Sm::kTile + (size_t)Sm::kRows * 4);
-  double* x_s = c_s + Sm::kRows;
-  double* Gs = x_s + LD;
-  double* delta_s = Gs + 256;
-
-  const int row = order[first + slot];
-  const int64_t p0 = a.ptr[row];
-  const int n = (int)(a.ptr[row + 1] - p0);
-  const int n_pad = (n + 3) & ~3;
-  const int grow = a.row_base + row;
-  double* xrow = a.X + (size_t)grow * LD;
-  const int K = a.K;
-  const double wi_row = USER ? 0.0 : a.Wi[grow];
-  const double g = USER ? 1.0 : wi_row;
-
-  double pr[MAXM], cw[MAXM], wr[MAXM];
-#pragma unroll
-  for (int m = 0; m < MAXM; m++) {
-    const int j = m * 32 + lane;
-    pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
-    if (j < n) {
-      const int id = a.idx[p0 + j];
-      idx_s[j] = id;
-      const double w = a.val ? a.val[p0 + j] : 1.0;
-      wr[m] = w * w;
-      cw[m] = w - (USER ? a.Wi[id] : wi_row);
-      if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
-    }
-    c_s[j] = cw[m];
+  // the S cache of the other side, resident in shared memory for the CTA's lifetime
+  const double* Sp = a.S;
+  if (Sm::kSInSmem) {
+    double* S_s = reinterpret_cast<double*>(smem);
+    for (int t = threadIdx.x; t < LD * LD / 2; t += blockDim.x)
+      reinterpret_cast<double2*>(S_s)[t] = __ldg(reinterpret_cast<const double2*>(a.S) + t);
+    Sp = S_s;
+    __syncthreads();
   }
-  for (int k = lane; k < LD; k += 32) x_s[k] = xrow[k];
-  __syncwarp();
 
+  unsigned char* base = smem + Sm::kS + (size_t)warp * Sm::kBytesPerWarp;
+  unsigned char* tile = base;
+  int* idx_s = reinterpret_cast<int*>(base + Sm::kTile);
+  double* c_s = reinterpret_cast<double*>(base + Sm::kTile + (size_t)Sm::kRows * 4);
+  double* z_s = c_s + Sm::kRows;
+  double* x_s = z_s + Sm::kRows;
+  double* Gs = x_s + LD;
+  double* Pt = Gs + 256;
+  double* delta_s = Pt + 16;
+
+  const int K = a.K;
   const int nblocks = (K + kFB - 1) / kFB;
+  const int f = lane & 15, hh = lane >> 4;
 
-  if (!a.use_cache) {   // prediction cache from scratch: p_j = <x, y_j>
+  for (int slot = blockIdx.x * wpb + warp; slot < count; slot += gridDim.x * wpb) {
+    const int row = order[first + slot];
+    const int64_t p0 = a.ptr[row];
+    const int n = (int)(a.ptr[row + 1] - p0);
+    const int n_pad = (n + 3) & ~3;
+    const int grow = a.row_base + row;
+    double* xrow = a.X + (size_t)grow * LD;
+    const double wi_row = USER ? 0.0 : a.Wi[grow];
+    const double g = USER ? 1.0 : wi_row;
+
+    double pr[MAXM], cw[MAXM], wr[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; m++) {
+      const int j = m * 32 + lane;
+      pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
+      if (j < n) {
+        const int id = a.idx[p0 + j];
+        idx_s[j] = id;
+        const double w = a.val ? a.val[p0 + j] : 1.0;
+        wr[m] = w * w;
+        cw[m] = w - (USER ? a.Wi[id] : wi_row);
+        if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
+      }
+      c_s[j] = cw[m];
+      z_s[j] = 0.0;
+    }
+    for (int k = lane; k < LD; k += 32) x_s[k] = xrow[k];
+    __syncwarp();
+
+    if (!a.use_cache) {   // prediction cache from scratch: p_j = <x, y_j>
+      for (int fb = 0; fb < nblocks; fb++) {
+        stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, lane, 32);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MAXM; m++) {
+          const int j = m * 32 + lane;
+          if (j < n) {
+            double y[16];
+            load_tile_row(tile, j, y);
+            double acc = pr[m];
+#pragma unroll
+            for (int e = 0; e < 16; e++) acc += x_s[fb * kFB + e] * y[e];
+            pr[m] = acc;
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, 0, lane, 32);
+    cp_async_commit();
     for (int fb = 0; fb < nblocks; fb++) {
-      stage_tile_async<LD>(tile0, idx_s, a.Y, n, n_pad, fb, lane, 32);
-      cp_async_commit();
+      const int f0 = fb * kFB;
+#pragma unroll
+      for (int m = 0; m < MAXM; m++) {
+        const int j = m * 32 + lane;
+        if (j < n) z_s[j] = wr[m] - cw[m] * pr[m];
+      }
+      // S.x for this block while the tile is in flight: t_f = sum_k x_k S[k][f0+f]
+      double tsum;
+      {
+        const double* __restrict__ Sc = Sp + (size_t)(hh * (LD / 2)) * LD + f0 + f;
+        const double* __restrict__ xh = x_s + hh * (LD / 2);
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;   // four independent chains
+#pragma unroll 2
+        for (int k = 0; k < LD / 2; k += 4) {
+          const double2 xa = *reinterpret_cast<const double2*>(xh + k);
+          const double2 xb = *reinterpret_cast<const double2*>(xh + k + 2);
+          t0 += xa.x * Sc[(size_t)k * LD];
+          t1 += xa.y * Sc[(size_t)(k + 1) * LD];
+          t2 += xb.x * Sc[(size_t)(k + 2) * LD];
+          t3 += xb.y * Sc[(size_t)(k + 3) * LD];
+        }
+        tsum = (t0 + t1) + (t2 + t3);
+        tsum += __shfl_xor_sync(kFullMask, tsum, 16);
+      }
       cp_async_wait<0>();
       __syncwarp();
+
+      double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      gram_rhs_fragments(tile, c_s, z_s, n_pad, frag);
+      // H = G + g S_BB, full symmetric 16 x 16, and P
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+#pragma unroll
+        for (int ii = 0; ii < 2; ii++) {
+          int rw = lane >> 2, cl = 2 * (lane & 3) + ii;
+          if (t >= 1) rw += 8;
+          if (t == 2) cl += 8;
+          const double v = frag[2 * t + ii] + g * Sp[(size_t)(f0 + rw) * LD + f0 + cl];
+          Gs[rw * 16 + cl] = v;
+          if (t == 1) Gs[cl * 16 + rw] = v;
+        }
+      }
+      if ((lane & 3) == 0) {
+        Pt[lane >> 2] = frag[6];
+        Pt[8 + (lane >> 2)] = frag[8];
+      }
+      __syncwarp();
+
+      // in-block Gauss-Seidel, lane f (both half-warps compute the same thing)
+      double h[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + f];
+      const double hff = Gs[f * 16 + f];
+      const double xf = x_s[f0 + f];
+      double numer = Pt[f] - g * tsum + xf * hff;
+      const double rden = 1.0 / (hff + a.reg);
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        const double d = numer * rden - xf;
+        const double ds = __shfl_sync(kFullMask, d, s);
+        if (f > s) numer -= ds * h[s];
+      }
+      const double xnew = numer * rden;
+      if (lane < 16) {
+        const bool livef = f0 + f < K;
+        if (livef) x_s[f0 + f] = xnew;
+        delta_s[f] = livef ? xnew - xf : 0.0;
+      }
+      __syncwarp();
+
+      double d[16];
+#pragma unroll
+      for (int e = 0; e < 16; e++) d[e] = delta_s[e];
 #pragma unroll
       for (int m = 0; m < MAXM; m++) {
         const int j = m * 32 + lane;
         if (j < n) {
           double y[16];
-          load_tile_row(tile0, j, y);
-          double acc = pr[m];
+          load_tile_row(tile, j, y);
+          double a0 = pr[m], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-          for (int e = 0; e < 16; e++) acc += x_s[fb * kFB + e] * y[e];
-          pr[m] = acc;
+          for (int e = 0; e < 16; e += 4) {
+            a0 += d[e] * y[e];
+            a1 += d[e + 1] * y[e + 1];
+            a2 += d[e + 2] * y[e + 2];
+            a3 += d[e + 3] * y[e + 3];
+          }
+          pr[m] = (a0 + a1) + (a2 + a3);
         }
       }
       __syncwarp();
-    }
-  }
-
-  stage_tile_async<LD>(tile0, idx_s, a.Y, n, n_pad, 0, lane, 32);
-  cp_async_commit();
-  for (int fb = 0; fb < nblocks; fb++) {
-    unsigned char* tile = tile0 + (NBUF == 2 ? (size_t)(fb & 1) * Sm::kTile : 0);
-    if (NBUF == 2 && fb + 1 < nblocks) {
-      stage_tile_async<LD>(tile0 + (size_t)((fb + 1) & 1) * Sm::kTile, idx_s, a.Y, n, n_pad, fb + 1, lane, 32);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncwarp();
-
-    double pp[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) pp[e] = 0.0;
-#pragma unroll
-    for (int m = 0; m < MAXM; m++) {
-      const int j = m * 32 + lane;
-      if (j < n) {
-        double y[16];
-        load_tile_row(tile, j, y);
-        const double z = wr[m] - cw[m] * pr[m];
-#pragma unroll
-        for (int e = 0; e < 16; e++) pp[e] += z * y[e];
+      if (fb + 1 < nblocks) {
+        stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb + 1, lane, 32);
+        cp_async_commit();
       }
     }
-    double frag[6] = {0, 0, 0, 0, 0, 0};
-    gram_fragments(tile, c_s, 0, n_pad, frag);
+    for (int k = lane; k < K; k += 32) xrow[k] = x_s[k];
+    if (a.pcache) {
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
-      scatter_partial(t * 64 + lane * 2, frag[2 * t], Gs, delta_s);
-      scatter_partial(t * 64 + lane * 2 + 1, frag[2 * t + 1], Gs, delta_s);
-    }
-    __syncwarp();
-    solve_block<LD>(x_s, Gs, pp, delta_s, a.S, fb * kFB, K, g, a.reg);
-    __syncwarp();
-    double d[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) d[e] = delta_s[e];
-#pragma unroll
-    for (int m = 0; m < MAXM; m++) {
-      const int j = m * 32 + lane;
-      if (j < n) {
-        double acc = pr[m];
-        double y[16];
-        load_tile_row(tile, j, y);
-#pragma unroll
-        for (int e = 0; e < 16; e++) acc += d[e] * y[e];
-        pr[m] = acc;
+      for (int m = 0; m < MAXM; m++) {
+        const int j = m * 32 + lane;
+        if (j < n) a.pcache[cache_pos(a, p0 + j)] = pr[m];
       }
     }
     __syncwarp();
-    if (NBUF == 1 && fb + 1 < nblocks) {
-      stage_tile_async<LD>(tile0, idx_s, a.Y, n, n_pad, fb + 1, lane, 32);
-      cp_async_commit();
-    }
-  }
-  for (int k = lane; k < K; k += 32) xrow[k] = x_s[k];
-  if (a.pcache) {
-#pragma unroll
-    for (int m = 0; m < MAXM; m++) {
-      const int j = m * 32 + lane;
-      if (j < n) a.pcache[cache_pos(a, p0 + j)] = pr[m];
-    }
   }
 }
 

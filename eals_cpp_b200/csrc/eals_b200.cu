@@ -462,16 +462,18 @@ int launch_cd_warp(eals_model* m, const CdSide& a, const int32_t* order, int fir
 template <int LD, int MAXM, bool USER>
 int launch_cd_warp_block(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
   if (count <= 0) return EALS_OK;
-  constexpr int NBUF = MAXM <= 2 ? 2 : 1;
-  using Sm = eals::WarpBlockSmem<LD, MAXM, NBUF>;
-  // as many warps per CTA as fit ~100 KB, so that two CTAs share an SM
-  int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (100 * 1024) / Sm::kBytesPerWarp));
+  using Sm = eals::WarpBlockSmem<LD, MAXM>;
+  // persistent CTAs, one per SM: S cache + as many row-warps as fit the 227 KB of shared memory
+  const size_t budget = 227 * 1024 - Sm::kS;
+  int wpb = (int)std::min<size_t>(12, std::max<size_t>(1, budget / Sm::kBytesPerWarp));
   static int env_wpb = getenv("EALS_WARP_WPB") ? atoi(getenv("EALS_WARP_WPB")) : 0;
-  if (env_wpb > 0) wpb = std::min(env_wpb, 8);
-  const size_t smem = Sm::kBytesPerWarp * wpb;
-  auto kern = eals::cd_warp_block_kernel<LD, MAXM, NBUF, USER>;
+  if (env_wpb > 0) wpb = std::min(env_wpb, wpb);
+  const size_t smem = Sm::kS + Sm::kBytesPerWarp * wpb;
+  auto kern = eals::cd_warp_block_kernel<LD, MAXM, USER>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(count + wpb - 1) / wpb, wpb * 32, smem, m->stream>>>(a, order, first, count);
+  const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / smem));
+  const int grid = std::min((count + wpb - 1) / wpb, m->sm_count * std::min(ctas_per_sm, 4));
+  kern<<<grid, wpb * 32, smem, m->stream>>>(a, order, first, count);
   return check_launch(m);
 }
 
