@@ -226,11 +226,11 @@ struct WarpBlockSmem {
 // Gram + right-hand-side fragments of tile rows [0, r1): frag[0..5] as gram_fragments, frag[6..7] =
 // P rows 0..7, frag[8..9] = P rows 8..15 (column 0 of each tile holds the sums).
 __device__ __forceinline__ void gram_rhs_fragments(const unsigned char* tile, const double* c_s, const double* z_s,
-                                                   int r1, double (&frag)[10]) {
+                                                   int r0, int r1, double (&frag)[10]) {
   const int lane = lane_id();
   const int rr = lane & 3, e0 = lane >> 2;
   const uint32_t off_lo = (uint32_t)(rr * 128 + ((e0 & 1) << 3));
-  for (int j0 = 0; j0 < r1; j0 += 4) {
+  for (int j0 = r0; j0 < r1; j0 += 4) {
     const int r = j0 + rr;
     const uint32_t sw = (uint32_t)(r & 7);
     const unsigned char* rowp = tile + (size_t)j0 * 128 + off_lo;
@@ -361,7 +361,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
       __syncwarp();
 
       double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      gram_rhs_fragments(tile, c_s, z_s, n_pad, frag);
+      gram_rhs_fragments(tile, c_s, z_s, 0, n_pad, frag);
       // H = G + g S_BB, full symmetric 16 x 16, and P
 #pragma unroll
       for (int t = 0; t < 3; t++) {
@@ -442,34 +442,43 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// One CTA per row, 129 .. 256*MW nonzeros.  Thread t owns nonzeros t, t+256, ...; warp w feeds tile
-// rows [w*32*MW, (w+1)*32*MW) to the tensor cores.
+// One CTA (8 warps) per row, 129 .. 256*MW nonzeros.  Thread t owns nonzeros t, t+256, ...; warp w
+// feeds tile rows [w*32*MW, (w+1)*32*MW) to the tensor cores (Gram + right-hand side, 5 tiles per 4
+// nonzeros).  The S.x term of the block is spread over ALL threads (thread = (factor, 1/16th of k))
+// and issued before the wait on the tile, so its loads overlap the gather; warp 0 then only runs
+// the 16-step multiply/shuffle/fma recurrence.
+// First version of this kernel (profiles r01b): 143 registers -> 1 CTA/SM, barrier stall 7.8 per
+// issue while warp 0 did the whole solve incl. 64 S loads per lane.  Now capped at 128 registers
+// (2 CTAs/SM up to 512 nonzeros).
 // ---------------------------------------------------------------------------------------------
 template <int LD, int MW>
 struct RowBlockSmem {
   static constexpr int kRows = kBlkThreads * MW;
   static constexpr size_t kTile = (size_t)kRows * 128;
   static constexpr size_t kIdx = (size_t)kRows * 4;
-  static constexpr size_t kC = (size_t)kRows * 8;
+  static constexpr size_t kCZ = (size_t)kRows * 16;           // c and z
   static constexpr size_t kX = (size_t)LD * 8;
   static constexpr size_t kSlots = (size_t)kBlkWarps * kPartLen * 8;
-  static constexpr size_t kSmall = (256 + 16 + 16) * 8;
-  static constexpr size_t kBytes = kTile + kIdx + kC + kX + kSlots + kSmall;
+  static constexpr size_t kSmall = (256 + 16 + 16 + 16 + 16 * 16) * 8;   // Gs, Pt, Tt, delta, tpart[16][16]
+  static constexpr size_t kBytes = kTile + kIdx + kCZ + kX + kSlots + kSmall;
 };
 
 template <int LD, int MW, bool USER>
-__global__ void __launch_bounds__(kBlkThreads)
+__global__ void __launch_bounds__(kBlkThreads, 2)
 cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   extern __shared__ __align__(128) unsigned char smem[];
   using Sm = RowBlockSmem<LD, MW>;
   unsigned char* tile = smem;
   int* idx_s = reinterpret_cast<int*>(smem + Sm::kTile);
   double* c_s = reinterpret_cast<double*>(smem + Sm::kTile + Sm::kIdx);
-  double* x_s = c_s + Sm::kRows;
+  double* z_s = c_s + Sm::kRows;
+  double* x_s = z_s + Sm::kRows;
   double* slots = x_s + LD;
   double* Gs = slots + kBlkWarps * kPartLen;
   double* Pt = Gs + 256;
-  double* delta_s = Pt + 16;
+  double* Tt = Pt + 16;
+  double* delta_s = Tt + 16;
+  double* tpart = delta_s + 16;    // [16 parts][16 factors]
 
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const int row = order[first + blockIdx.x];
@@ -495,7 +504,8 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       cw[m] = w - (USER ? a.Wi[id] : wi_row);
       if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
     }
-    if (j < Sm::kRows) c_s[j] = cw[m];
+    c_s[j] = cw[m];
+    z_s[j] = 0.0;
   }
   for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
   __syncthreads();
@@ -524,66 +534,117 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   }
 
   // Pass 2: one blocked update per 16 factors
-  const int w_r0 = warp * 32 * MW;
-  const int w_r1 = min(w_r0 + 32 * MW, n_pad);
+  const int w_r1 = min((warp + 1) * 32 * MW, n_pad);
+  const int tf = tid & 15, tpart_id = tid >> 4;          // S.x: factor and 1/16th of the k range
+  constexpr int kPer = LD / 16;                           // k's per thread
+  stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, 0, tid, kBlkThreads);
+  cp_async_commit();
   for (int fb = 0; fb < nblocks; fb++) {
-    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-
-    double pp[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) pp[e] = 0.0;
+    const int f0 = fb * kFB;
 #pragma unroll
     for (int m = 0; m < MW; m++) {
       const int j = m * kBlkThreads + tid;
-      if (j < n) {
-        double y[16];
-        load_tile_row(tile, j, y);
-        const double z = wr[m] - cw[m] * pr[m];
-#pragma unroll
-        for (int e = 0; e < 16; e++) pp[e] += z * y[e];
-      }
+      if (j < n) z_s[j] = wr[m] - cw[m] * pr[m];
     }
-    const double ptot = warp_reduce16(pp);
-    double frag[6] = {0, 0, 0, 0, 0, 0};
-    gram_fragments(tile, c_s, w_r0, w_r1, frag);
+    {   // partial t_f = sum over this thread's k's of x_k S[k][f0+f] (S symmetric: unit stride over f)
+      const double* __restrict__ Sc = a.S + (size_t)(tpart_id * kPer) * LD + f0 + tf;
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPer; k += 2) {
+        t0 += x_s[tpart_id * kPer + k] * __ldg(Sc + (size_t)k * LD);
+        if (kPer > 1) t1 += x_s[tpart_id * kPer + k + 1] * __ldg(Sc + (size_t)(k + 1) * LD);
+      }
+      tpart[tpart_id * 16 + tf] = t0 + t1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    gram_rhs_fragments(tile, c_s, z_s, warp * 32 * MW, w_r1, frag);
     double* slot = slots + warp * kPartLen;
 #pragma unroll
     for (int t = 0; t < 3; t++) {
       slot[t * 64 + lane * 2] = frag[2 * t];
       slot[t * 64 + lane * 2 + 1] = frag[2 * t + 1];
     }
-    if ((lane & 1) == 0) slot[192 + (lane >> 1)] = ptot;
+    if ((lane & 3) == 0) {
+      slot[192 + (lane >> 2)] = frag[6];
+      slot[200 + (lane >> 2)] = frag[8];
+    }
     __syncthreads();
     if (tid < kPartLen) {
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < kBlkWarps; w++) s += slots[w * kPartLen + tid];
-      scatter_partial(tid, s, Gs, Pt);
+      if (tid < 192) {   // H = G + g S_BB
+        const int t = tid >> 6, l = (tid & 63) >> 1, ii = tid & 1;
+        int rw = l >> 2, cl = 2 * (l & 3) + ii;
+        if (t >= 1) rw += 8;
+        if (t == 2) cl += 8;
+        s += g * __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
+        Gs[rw * 16 + cl] = s;
+        if (t == 1) Gs[cl * 16 + rw] = s;
+      } else {
+        Pt[tid - 192] = s;
+      }
+    } else if (tid < kPartLen + 16) {
+      const int ff = tid - kPartLen;
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; q++) s += tpart[q * 16 + ff];
+      Tt[ff] = s;
     }
     __syncthreads();
     if (warp == 0) {
-      double pt[16];
+      const int ff = lane & 15;
+      double h[16];
 #pragma unroll
-      for (int e = 0; e < 16; e++) pt[e] = lane == 0 ? Pt[e] : 0.0;
-      solve_block<LD>(x_s, Gs, pt, delta_s, a.S, fb * kFB, K, g, a.reg);
-    }
-    __syncthreads();
+      for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + ff];
+      const double hff = Gs[ff * 16 + ff];
+      const double xf = x_s[f0 + ff];
+      double numer = Pt[ff] - g * Tt[ff] + xf * hff;
+      const double rden = 1.0 / (hff + a.reg);
 #pragma unroll
-    for (int m = 0; m < MW; m++) {
-      const int j = m * kBlkThreads + tid;
-      if (j < n) {
-        double y[16];
-        load_tile_row(tile, j, y);
-        double acc = pr[m];
-#pragma unroll
-        for (int e = 0; e < 16; e++) acc += delta_s[e] * y[e];
-        pr[m] = acc;
+      for (int sidx = 0; sidx < 16; sidx++) {
+        const double d = numer * rden - xf;
+        const double ds = __shfl_sync(kFullMask, d, sidx);
+        if (ff > sidx) numer -= ds * h[sidx];
+      }
+      const double xnew = numer * rden;
+      if (lane < 16) {
+        const bool livef = f0 + ff < K;
+        if (livef) x_s[f0 + ff] = xnew;
+        delta_s[ff] = livef ? xnew - xf : 0.0;
       }
     }
     __syncthreads();
+    {
+      double d[16];
+#pragma unroll
+      for (int e = 0; e < 16; e++) d[e] = delta_s[e];
+#pragma unroll
+      for (int m = 0; m < MW; m++) {
+        const int j = m * kBlkThreads + tid;
+        if (j < n) {
+          double y[16];
+          load_tile_row(tile, j, y);
+          double a0 = pr[m], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            a0 += d[e] * y[e];
+            a1 += d[e + 1] * y[e + 1];
+            a2 += d[e + 2] * y[e + 2];
+            a3 += d[e + 3] * y[e + 3];
+          }
+          pr[m] = (a0 + a1) + (a2 + a3);
+        }
+      }
+    }
+    __syncthreads();
+    if (fb + 1 < nblocks) {
+      stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb + 1, tid, kBlkThreads);
+      cp_async_commit();
+    }
   }
   for (int k = tid; k < K; k += kBlkThreads) xrow[k] = x_s[k];
   if (a.pcache) {

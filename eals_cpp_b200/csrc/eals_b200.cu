@@ -63,7 +63,9 @@ int dev_alloc(T** p, size_t n) {
 // 1..3: warp per row (1/2/4 nonzeros per lane); 4..6: one CTA per row, blocked CD (1/2/4 nonzeros
 // per thread); 7: heavy rows, split into slabs.
 constexpr int kNumBuckets = 8;
-constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 128, 256, 512, 1024, 0x7fffffff};
+// bucket 6 is kept empty: measured on c4, rows of 513..1024 nonzeros run faster through the slab
+// pipeline (0.5 ns/nnz) than as one CTA per SM (1 ns/nnz).
+constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 128, 256, 512, 512, 0x7fffffff};
 constexpr int kMidBucket = 4;     // first one-CTA-per-row bucket
 constexpr int kHeavyBucket = 7;
 // Heavy rows per launch group.  Measured on c4 (profiles/README.md r01b): launch granularity matters
@@ -551,8 +553,7 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     if (n <= 64) return launch_cd_warp_block<LD, 2, USER>(m, a, one, 0, 1);
     if (n <= 128) return launch_cd_warp_block<LD, 4, USER>(m, a, one, 0, 1);
     if (n <= 256) return launch_cd_row_block<LD, 1, USER>(m, a, one, 0, 1);
-    if (n <= 512) return launch_cd_row_block<LD, 2, USER>(m, a, one, 0, 1);
-    return launch_cd_row_block<LD, 4, USER>(m, a, one, 0, 1);
+    return launch_cd_row_block<LD, 2, USER>(m, a, one, 0, 1);
   }
   // heavy rows first: their launch chain is the longest
   const int t0 = USER ? T_U_HEAVY : T_I_HEAVY;
@@ -560,7 +561,6 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   for (const HeavyBatch& b : s.batches) OK((run_heavy_batch<LD, USER>(m, s, a, b)));
   toc(m, t0);
   tic(m, t0 + 1);
-  OK((launch_cd_row_block<LD, 4, USER>(m, a, s.order, s.first[6], s.first[7] - s.first[6])));
   OK((launch_cd_row_block<LD, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));
   OK((launch_cd_row_block<LD, 1, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
   toc(m, t0 + 1);
