@@ -442,7 +442,8 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// One CTA (8 warps) per row, 129 .. 256*MW nonzeros.  Thread t owns nonzeros t, t+256, ...; warp w
+// One CTA (a team of TW = 2, 4 or 8 warps) per row of up to 32*TW*MW nonzeros.  Thread t owns
+// nonzeros t, t+32*TW, ...; warp w
 // feeds tile rows [w*32*MW, (w+1)*32*MW) to the tensor cores (Gram + right-hand side, 5 tiles per 4
 // nonzeros).  The S.x term of the block is spread over ALL threads (thread = (factor, 1/16th of k))
 // and issued before the wait on the tile, so its loads overlap the gather; warp 0 then only runs
@@ -451,34 +452,38 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 // issue while warp 0 did the whole solve incl. 64 S loads per lane.  Now capped at 128 registers
 // (2 CTAs/SM up to 512 nonzeros).
 // ---------------------------------------------------------------------------------------------
-template <int LD, int MW>
+template <int LD, int TW, int MW>
 struct RowBlockSmem {
-  static constexpr int kRows = kBlkThreads * MW;
+  static constexpr int kT = TW * 32;                         // threads per CTA (team of TW warps)
+  static constexpr int kRows = kT * MW;
   static constexpr size_t kTile = (size_t)kRows * 128;
   static constexpr size_t kIdx = (size_t)kRows * 4;
   static constexpr size_t kCZ = (size_t)kRows * 16;           // c and z
   static constexpr size_t kX = (size_t)LD * 8;
-  static constexpr size_t kSlots = (size_t)kBlkWarps * kPartLen * 8;
-  static constexpr size_t kSmall = (256 + 16 + 16 + 16 + 16 * 16) * 8;   // Gs, Pt, Tt, delta, tpart[16][16]
+  static constexpr size_t kSlots = (size_t)TW * kPartLen * 8;
+  static constexpr size_t kSmall = (256 + 16 + 16 + 16 + 16 * 16) * 8;   // Gs, Pt, Tt, delta, tpart[<=16][16]
   static constexpr size_t kBytes = kTile + kIdx + kCZ + kX + kSlots + kSmall;
 };
 
-template <int LD, int MW, bool USER>
-__global__ void __launch_bounds__(kBlkThreads, 2)
+template <int LD, int TW, int MW, bool USER>
+__global__ void __launch_bounds__(TW * 32, 16 / TW)
 cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   extern __shared__ __align__(128) unsigned char smem[];
-  using Sm = RowBlockSmem<LD, MW>;
+  using Sm = RowBlockSmem<LD, TW, MW>;
+  constexpr int kT = TW * 32;
+  constexpr int kParts = kT / 16;                            // S.x: threads = (factor, part of the k range)
+  static_assert(kPartLen + 16 <= kT || TW < 8, "reduction threads");
   unsigned char* tile = smem;
   int* idx_s = reinterpret_cast<int*>(smem + Sm::kTile);
   double* c_s = reinterpret_cast<double*>(smem + Sm::kTile + Sm::kIdx);
   double* z_s = c_s + Sm::kRows;
   double* x_s = z_s + Sm::kRows;
   double* slots = x_s + LD;
-  double* Gs = slots + kBlkWarps * kPartLen;
+  double* Gs = slots + TW * kPartLen;
   double* Pt = Gs + 256;
   double* Tt = Pt + 16;
   double* delta_s = Tt + 16;
-  double* tpart = delta_s + 16;    // [16 parts][16 factors]
+  double* tpart = delta_s + 16;    // [kParts][16 factors]
 
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const int row = order[first + blockIdx.x];
@@ -494,7 +499,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   double pr[MW], cw[MW], wr[MW];
 #pragma unroll
   for (int m = 0; m < MW; m++) {
-    const int j = m * kBlkThreads + tid;
+    const int j = m * kT + tid;
     pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
     if (j < n) {
       const int id = a.idx[p0 + j];
@@ -507,20 +512,20 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
     c_s[j] = cw[m];
     z_s[j] = 0.0;
   }
-  for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
+  for (int k = tid; k < LD; k += kT) x_s[k] = xrow[k];
   __syncthreads();
 
   const int nblocks = (K + kFB - 1) / kFB;
 
   // Pass 1: prediction cache p_j = <x, y_j> (skipped when the symmetric cache is valid)
   for (int fb = 0; fb < (a.use_cache ? 0 : nblocks); fb++) {
-    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
+    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kT);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
 #pragma unroll
     for (int m = 0; m < MW; m++) {
-      const int j = m * kBlkThreads + tid;
+      const int j = m * kT + tid;
       if (j < n) {
         double y[16];
         load_tile_row(tile, j, y);
@@ -536,20 +541,20 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   // Pass 2: one blocked update per 16 factors
   const int w_r1 = min((warp + 1) * 32 * MW, n_pad);
   const int tf = tid & 15, tpart_id = tid >> 4;          // S.x: factor and 1/16th of the k range
-  constexpr int kPer = LD / 16;                           // k's per thread
-  stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, 0, tid, kBlkThreads);
+  constexpr int kPer = LD / kParts;                       // k's per thread
+  stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, 0, tid, kT);
   cp_async_commit();
   for (int fb = 0; fb < nblocks; fb++) {
     const int f0 = fb * kFB;
 #pragma unroll
     for (int m = 0; m < MW; m++) {
-      const int j = m * kBlkThreads + tid;
+      const int j = m * kT + tid;
       if (j < n) z_s[j] = wr[m] - cw[m] * pr[m];
     }
     {   // partial t_f = sum over this thread's k's of x_k S[k][f0+f] (S symmetric: unit stride over f)
       const double* __restrict__ Sc = a.S + (size_t)(tpart_id * kPer) * LD + f0 + tf;
       double t0 = 0.0, t1 = 0.0;
-#pragma unroll
+#pragma unroll 8
       for (int k = 0; k < kPer; k += 2) {
         t0 += x_s[tpart_id * kPer + k] * __ldg(Sc + (size_t)k * LD);
         if (kPer > 1) t1 += x_s[tpart_id * kPer + k + 1] * __ldg(Sc + (size_t)(k + 1) * LD);
@@ -572,27 +577,29 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       slot[200 + (lane >> 2)] = frag[8];
     }
     __syncthreads();
-    if (tid < kPartLen) {
-      double s = 0.0;
+    for (int i = tid; i < kPartLen + 16; i += kT) {
+      if (i < kPartLen) {
+        double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < kBlkWarps; w++) s += slots[w * kPartLen + tid];
-      if (tid < 192) {   // H = G + g S_BB
-        const int t = tid >> 6, l = (tid & 63) >> 1, ii = tid & 1;
-        int rw = l >> 2, cl = 2 * (l & 3) + ii;
-        if (t >= 1) rw += 8;
-        if (t == 2) cl += 8;
-        s += g * __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
-        Gs[rw * 16 + cl] = s;
-        if (t == 1) Gs[cl * 16 + rw] = s;
+        for (int w = 0; w < TW; w++) s += slots[w * kPartLen + i];
+        if (i < 192) {   // H = G + g S_BB
+          const int t = i >> 6, l = (i & 63) >> 1, ii = i & 1;
+          int rw = l >> 2, cl = 2 * (l & 3) + ii;
+          if (t >= 1) rw += 8;
+          if (t == 2) cl += 8;
+          s += g * __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
+          Gs[rw * 16 + cl] = s;
+          if (t == 1) Gs[cl * 16 + rw] = s;
+        } else {
+          Pt[i - 192] = s;
+        }
       } else {
-        Pt[tid - 192] = s;
-      }
-    } else if (tid < kPartLen + 16) {
-      const int ff = tid - kPartLen;
-      double s = 0.0;
+        const int ff = i - kPartLen;
+        double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < 16; q++) s += tpart[q * 16 + ff];
-      Tt[ff] = s;
+        for (int q = 0; q < kParts; q++) s += tpart[q * 16 + ff];
+        Tt[ff] = s;
+      }
     }
     __syncthreads();
     if (warp == 0) {
@@ -624,7 +631,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       for (int e = 0; e < 16; e++) d[e] = delta_s[e];
 #pragma unroll
       for (int m = 0; m < MW; m++) {
-        const int j = m * kBlkThreads + tid;
+        const int j = m * kT + tid;
         if (j < n) {
           double y[16];
           load_tile_row(tile, j, y);
@@ -642,15 +649,15 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
     }
     __syncthreads();
     if (fb + 1 < nblocks) {
-      stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb + 1, tid, kBlkThreads);
+      stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb + 1, tid, kT);
       cp_async_commit();
     }
   }
-  for (int k = tid; k < K; k += kBlkThreads) xrow[k] = x_s[k];
+  for (int k = tid; k < K; k += kT) xrow[k] = x_s[k];
   if (a.pcache) {
 #pragma unroll
     for (int m = 0; m < MW; m++) {
-      const int j = m * kBlkThreads + tid;
+      const int j = m * kT + tid;
       if (j < n) a.pcache[cache_pos(a, p0 + j)] = pr[m];
     }
   }

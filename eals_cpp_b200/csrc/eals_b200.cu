@@ -479,13 +479,13 @@ int launch_cd_warp_block(eals_model* m, const CdSide& a, const int32_t* order, i
   return check_launch(m);
 }
 
-template <int LD, int MW, bool USER>
+template <int LD, int TW, int MW, bool USER>
 int launch_cd_row_block(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
   if (count <= 0) return EALS_OK;
-  using Sm = eals::RowBlockSmem<LD, MW>;
-  auto kern = eals::cd_row_block_kernel<LD, MW, USER>;
+  using Sm = eals::RowBlockSmem<LD, TW, MW>;
+  auto kern = eals::cd_row_block_kernel<LD, TW, MW, USER>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::kBytes));
-  kern<<<count, eals::kBlkThreads, Sm::kBytes, m->stream>>>(a, order, first);
+  kern<<<count, TW * 32, Sm::kBytes, m->stream>>>(a, order, first);
   return check_launch(m);
 }
 
@@ -550,10 +550,10 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     int32_t* one = reinterpret_cast<int32_t*>(m->partials);
     CU(cudaMemcpyAsync(one, &only_row, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
     if (n <= 32) return launch_cd_warp_block<LD, 1, USER>(m, a, one, 0, 1);
-    if (n <= 64) return launch_cd_warp_block<LD, 2, USER>(m, a, one, 0, 1);
-    if (n <= 128) return launch_cd_warp_block<LD, 4, USER>(m, a, one, 0, 1);
-    if (n <= 256) return launch_cd_row_block<LD, 1, USER>(m, a, one, 0, 1);
-    return launch_cd_row_block<LD, 2, USER>(m, a, one, 0, 1);
+    if (n <= 64) return launch_cd_row_block<LD, 2, 1, USER>(m, a, one, 0, 1);
+    if (n <= 128) return launch_cd_row_block<LD, 4, 1, USER>(m, a, one, 0, 1);
+    if (n <= 256) return launch_cd_row_block<LD, 8, 1, USER>(m, a, one, 0, 1);
+    return launch_cd_row_block<LD, 8, 2, USER>(m, a, one, 0, 1);
   }
   // heavy rows first: their launch chain is the longest
   const int t0 = USER ? T_U_HEAVY : T_I_HEAVY;
@@ -561,8 +561,8 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   for (const HeavyBatch& b : s.batches) OK((run_heavy_batch<LD, USER>(m, s, a, b)));
   toc(m, t0);
   tic(m, t0 + 1);
-  OK((launch_cd_row_block<LD, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));
-  OK((launch_cd_row_block<LD, 1, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
+  OK((launch_cd_row_block<LD, 8, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));
+  OK((launch_cd_row_block<LD, 8, 1, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
   toc(m, t0 + 1);
   tic(m, t0 + 2);
   static const bool seq = getenv("EALS_WARP_SEQ") && getenv("EALS_WARP_SEQ")[0] == '1';
@@ -571,8 +571,14 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
     OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
   } else {
-    OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
-    OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+    static const bool warp_only = getenv("EALS_WARP_ONLY") && getenv("EALS_WARP_ONLY")[0] == '1';
+    if (warp_only) {   // rows of 33..128 nonzeros as one warp each (comparison)
+      OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+      OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+    } else {           // ... or as teams of 4 / 2 warps
+      OK((launch_cd_row_block<LD, 4, 1, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+      OK((launch_cd_row_block<LD, 2, 1, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+    }
     OK((launch_cd_warp_block<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
   }
   toc(m, t0 + 2);
