@@ -43,7 +43,7 @@ namespace eals {
 constexpr int kBlkThreads = 256;
 constexpr int kBlkWarps = kBlkThreads / 32;
 constexpr int kPartLen = 208;   // 3 tiles x 32 lanes x 2 (C fragments) + 16 (P)
-constexpr int kSlab = 512;      // nonzeros per slab of a heavy row
+constexpr int kSlab = 256;      // nonzeros per slab of a heavy row (one per thread)
 
 // ---- swizzled tile: row r = 128 bytes, 16-byte chunk c stored at chunk position c ^ (r & 7) ----
 __device__ __forceinline__ uint32_t tile_chunk_off(int r, int c) { return (uint32_t)(r * 128 + (((c ^ r) & 7) << 4)); }
@@ -77,57 +77,6 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-// Sum v[0..16) over the warp; afterwards lanes 2f and 2f+1 hold the total of v[f] (returned).
-__device__ __forceinline__ double warp_reduce16(double (&v)[16]) {
-  const int lane = lane_id();
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const bool hi = lane & 16;
-    const double send = hi ? v[i] : v[i + 8];
-    const double keep = hi ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(kFullMask, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const bool hi = lane & 8;
-    const double send = hi ? v[i] : v[i + 4];
-    const double keep = hi ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(kFullMask, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    const bool hi = lane & 4;
-    const double send = hi ? v[i] : v[i + 2];
-    const double keep = hi ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(kFullMask, send, 4);
-  }
-  {
-    const bool hi = lane & 2;
-    const double send = hi ? v[0] : v[1];
-    const double keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(kFullMask, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(kFullMask, v[0], 1);
-}
-
-// One warp accumulates the Gram fragments of tile rows [r0, r1) (r0 a multiple of 4; rows past the
-// live count are zero with c = 0).  frag[0..1] = C00, [2..3] = C10, [4..5] = C11.
-__device__ __forceinline__ void gram_fragments(const unsigned char* tile, const double* c_s, int r0, int r1,
-                                               double (&frag)[6]) {
-  const int lane = lane_id();
-  const int rr = lane & 3, e0 = lane >> 2;
-  for (int j0 = r0; j0 < r1; j0 += 4) {
-    const int r = j0 + rr;
-    const double a0 = tile_elem(tile, r, e0);
-    const double a1 = tile_elem(tile, r, 8 + e0);
-    const double cj = c_s[r];
-    const double b0 = cj * a0, b1 = cj * a1;
-    dmma_884(frag[0], frag[1], a0, b0);
-    dmma_884(frag[2], frag[3], a1, b0);
-    dmma_884(frag[4], frag[5], a1, b1);
-  }
-}
-
 // Load the 16 doubles of tile row r into registers.
 __device__ __forceinline__ void load_tile_row(const unsigned char* tile, int r, double (&y)[16]) {
 #pragma unroll
@@ -135,66 +84,6 @@ __device__ __forceinline__ void load_tile_row(const unsigned char* tile, int r, 
     const double2 d = *reinterpret_cast<const double2*>(tile + tile_chunk_off(r, c));
     y[2 * c] = d.x;
     y[2 * c + 1] = d.y;
-  }
-}
-
-// Scatter a summed partial (fragment layout) into the full symmetric Gs[16][16] and Pt[16].
-__device__ __forceinline__ void scatter_partial(int i, double v, double* Gs, double* Pt) {
-  if (i < 192) {
-    const int t = i >> 6, l = (i & 63) >> 1, ii = i & 1;
-    int row = l >> 2, col = 2 * (l & 3) + ii;
-    if (t >= 1) row += 8;
-    if (t == 2) col += 8;
-    Gs[row * 16 + col] = v;
-    if (t == 1) Gs[col * 16 + row] = v;
-  } else if (i < kPartLen) {
-    Pt[i - 192] = v;
-  }
-}
-
-// The per-row, per-block solve, by ONE warp.  x_s: the row's K factors (shared, updated in place);
-// Gs: summed local Gram of the block; pp[f]: this lane's contribution to P_f (the warp total is
-// what counts: callers holding the total pass it in lane 0 and zeros elsewhere); delta_s[16]
-// receives d_f.  One reciprocal per factor (all 16 in parallel) replaces the reference's divide.
-template <int LD>
-__device__ __forceinline__ void solve_block(double* x_s, const double* Gs, double (&pp)[16], double* delta_s,
-                                            const double* __restrict__ S, int f0, int K, double g, double reg) {
-  const int lane = lane_id();
-  // t_f = sum_k x_k S[f0+f][k], k split over lanes; folded with P into base_f = P_f - g t_f
-  double tp[16];
-#pragma unroll
-  for (int f = 0; f < 16; f++) tp[f] = 0.0;
-  for (int k = lane; k < K; k += 32) {
-    const double xk = x_s[k];
-    const double* __restrict__ Sk = S + (size_t)f0 * LD + k;
-#pragma unroll
-    for (int f = 0; f < 16; f++) tp[f] += xk * __ldg(Sk + (size_t)f * LD);
-  }
-#pragma unroll
-  for (int f = 0; f < 16; f++) pp[f] -= g * tp[f];
-  const double base_pair = warp_reduce16(pp);                       // lanes 2f, 2f+1 hold base_f
-  const int f = lane & 15;
-  const double base = __shfl_sync(kFullMask, base_pair, 2 * f);
-  double h[16];
-  const double* __restrict__ Sb = S + (size_t)f0 * LD + f0 + f;
-#pragma unroll
-  for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + f] + g * __ldg(Sb + (size_t)k * LD);
-  const double xf = x_s[f0 + f];
-  const double hff = Gs[f * 16 + f] + g * __ldg(Sb + (size_t)f * LD);
-  double numer = base + xf * hff;
-  const double rden = 1.0 / (hff + reg);
-  double xnew = xf, mydelta = 0.0;
-#pragma unroll
-  for (int s = 0; s < 16; s++) {
-    const double cand = numer * rden;
-    const double d = cand - xf;
-    const double ds = __shfl_sync(kFullMask, d, s);
-    if (f == s) { xnew = cand; mydelta = d; }
-    if (f > s) numer -= ds * h[s];
-  }
-  if (lane < 16) {
-    if (f0 + f < K) x_s[f0 + f] = xnew;
-    delta_s[f] = (f0 + f < K) ? mydelta : 0.0;
   }
 }
 
@@ -713,27 +602,31 @@ heavy_pred_kernel(CdSide a, HeavyUnits hu, int u0, double* __restrict__ pred) {
 }
 
 struct HeavySmem {
-  static constexpr size_t kTile = (size_t)kSlab * 128;
+  static constexpr size_t kTile = (size_t)kSlab * 128;       // x2: previous block (cache update) + this block
   static constexpr size_t kIdx = (size_t)kSlab * 4;
-  static constexpr size_t kC = (size_t)kSlab * 8;
-  static constexpr size_t kSlots = (size_t)kBlkWarps * kPartLen * 8;
-  static constexpr size_t kBytes = kTile + kIdx + kC + kSlots + 16 * 8;
+  static constexpr size_t kCZ = (size_t)kSlab * 16;
+  // the per-warp reduction slots (8 x 208 doubles) reuse the previous-block tile once it is consumed
+  static constexpr size_t kBytes = 2 * kTile + kIdx + kCZ + 16 * 8;
 };
+static_assert((size_t)kBlkWarps * kPartLen * 8 <= HeavySmem::kTile, "slots must fit the spare tile");
 
 // Step fb of the batch: (1) if fb > 0, apply the cache update of block fb-1 (needs that block's
-// lines again — L2-resident by the batching) ; (2) if fb < nblocks, form the slab's partial Gram and
-// right-hand side of block fb and write them to partials[unit - u0].
+// lines again); (2) if fb < nblocks, form the slab's partial Gram and right-hand side of block fb
+// (tensor cores) and write them to partials[unit - u0].  Both tiles are requested up front (two
+// cp.async groups in flight), so a slab pays one memory round trip per step, not two.
 template <int LD, bool USER>
-__global__ void __launch_bounds__(kBlkThreads)
+__global__ void __launch_bounds__(kBlkThreads, 3)
 heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* __restrict__ pred,
                   const double* __restrict__ delta, double* __restrict__ partials) {
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* tile = smem;
-  int* idx_s = reinterpret_cast<int*>(smem + HeavySmem::kTile);
-  double* c_s = reinterpret_cast<double*>(smem + HeavySmem::kTile + HeavySmem::kIdx);
-  double* slots = c_s + kSlab;
-  double* delta_s = slots + kBlkWarps * kPartLen;
-  constexpr int MW = kSlab / kBlkThreads;
+  unsigned char* tile_prev = smem;
+  unsigned char* tile = smem + HeavySmem::kTile;
+  int* idx_s = reinterpret_cast<int*>(smem + 2 * HeavySmem::kTile);
+  double* c_s = reinterpret_cast<double*>(smem + 2 * HeavySmem::kTile + HeavySmem::kIdx);
+  double* z_s = c_s + kSlab;
+  double* delta_s = z_s + kSlab;
+  double* slots = reinterpret_cast<double*>(tile_prev);   // free again after the cache update
+  static_assert(kSlab == kBlkThreads, "one nonzero per thread");
 
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const int u = u0 + blockIdx.x;
@@ -744,89 +637,71 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   const int grow = a.row_base + row;
   const double wi_row = USER ? 0.0 : a.Wi[grow];
 
-  double pr[MW], cw[MW], wr[MW];
-#pragma unroll
-  for (int m = 0; m < MW; m++) {
-    const int j = m * kBlkThreads + tid;
-    pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
-    if (j < n) {
-      const int id = a.idx[off + j];
-      idx_s[j] = id;
-      const double w = a.val ? a.val[off + j] : 1.0;
-      wr[m] = w * w;
-      cw[m] = w - (USER ? a.Wi[id] : wi_row);
-      pr[m] = (fb == 0 && a.use_cache) ? a.pcache[cache_pos(a, off + j)] : pred[poff + j];
-    }
-    c_s[j] = cw[m];
+  double pr = 0.0, cw = 0.0, wr = 0.0;
+  if (tid < n) {
+    const int id = a.idx[off + tid];
+    idx_s[tid] = id;
+    const double w = a.val ? a.val[off + tid] : 1.0;
+    wr = w * w;
+    cw = w - (USER ? a.Wi[id] : wi_row);
+    pr = (fb == 0 && a.use_cache) ? a.pcache[cache_pos(a, off + tid)] : pred[poff + tid];
   }
+  c_s[tid] = cw;
   if (fb > 0 && tid < 16) delta_s[tid] = delta[(size_t)hu.unit_hrow[u] * 16 + tid];
   __syncthreads();
 
   if (fb > 0) {
-    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb - 1, tid, kBlkThreads);
+    stage_tile_async<LD>(tile_prev, idx_s, a.Y, n, n_pad, fb - 1, tid, kBlkThreads);
     cp_async_commit();
-    cp_async_wait<0>();
+  }
+  if (fb < nblocks) {
+    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
+    cp_async_commit();
+  }
+  if (fb > 0) {
+    if (fb < nblocks) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    if (tid < n) {
+      double y[16];
+      load_tile_row(tile_prev, tid, y);
+      double a0 = pr, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-    for (int m = 0; m < MW; m++) {
-      const int j = m * kBlkThreads + tid;
-      if (j < n) {
-        double y[16];
-        load_tile_row(tile, j, y);
-        double acc = pr[m];
-#pragma unroll
-        for (int e = 0; e < 16; e++) acc += delta_s[e] * y[e];
-        pr[m] = acc;
-        if (fb < nblocks) pred[poff + j] = acc;
-        else if (a.pcache) a.pcache[cache_pos(a, off + j)] = acc;   // final value -> symmetric cache
+      for (int e = 0; e < 16; e += 4) {
+        a0 += delta_s[e] * y[e];
+        a1 += delta_s[e + 1] * y[e + 1];
+        a2 += delta_s[e + 2] * y[e + 2];
+        a3 += delta_s[e + 3] * y[e + 3];
       }
+      pr = (a0 + a1) + (a2 + a3);
+      if (fb < nblocks) pred[poff + tid] = pr;
+      else if (a.pcache) a.pcache[cache_pos(a, off + tid)] = pr;   // final value -> symmetric cache
     }
-    __syncthreads();
+  } else if (a.use_cache && tid < n) {
+    pred[poff + tid] = pr;   // the pipeline's compact cache starts from the symmetric one
   }
   if (fb >= nblocks) return;
-  if (fb == 0 && a.use_cache) {   // the pipeline's compact cache starts from the symmetric one
-#pragma unroll
-    for (int m = 0; m < MW; m++) {
-      const int j = m * kBlkThreads + tid;
-      if (j < n) pred[poff + j] = pr[m];
-    }
-  }
-
-  stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
-  cp_async_commit();
+  z_s[tid] = tid < n ? wr - cw * pr : 0.0;
   cp_async_wait<0>();
   __syncthreads();
-  double pp[16];
-#pragma unroll
-  for (int e = 0; e < 16; e++) pp[e] = 0.0;
-#pragma unroll
-  for (int m = 0; m < MW; m++) {
-    const int j = m * kBlkThreads + tid;
-    if (j < n) {
-      double y[16];
-      load_tile_row(tile, j, y);
-      const double z = wr[m] - cw[m] * pr[m];
-#pragma unroll
-      for (int e = 0; e < 16; e++) pp[e] += z * y[e];
-    }
-  }
-  const double ptot = warp_reduce16(pp);
-  double frag[6] = {0, 0, 0, 0, 0, 0};
-  const int w_r0 = warp * 32 * MW;
-  gram_fragments(tile, c_s, w_r0, min(w_r0 + 32 * MW, n_pad), frag);
+
+  double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  gram_rhs_fragments(tile, c_s, z_s, warp * 32, min(warp * 32 + 32, n_pad), frag);
   double* slot = slots + warp * kPartLen;
 #pragma unroll
   for (int t = 0; t < 3; t++) {
     slot[t * 64 + lane * 2] = frag[2 * t];
     slot[t * 64 + lane * 2 + 1] = frag[2 * t + 1];
   }
-  if ((lane & 1) == 0) slot[192 + (lane >> 1)] = ptot;
+  if ((lane & 3) == 0) {
+    slot[192 + (lane >> 2)] = frag[6];
+    slot[200 + (lane >> 2)] = frag[8];
+  }
   __syncthreads();
   if (tid < kPartLen) {
-    double s = 0.0;
+    double sum = 0.0;
 #pragma unroll
-    for (int w = 0; w < kBlkWarps; w++) s += slots[w * kPartLen + tid];
-    partials[(size_t)(u - u0) * kPartLen + tid] = s;
+    for (int w = 0; w < kBlkWarps; w++) sum += slots[w * kPartLen + tid];
+    partials[(size_t)(u - u0) * kPartLen + tid] = sum;
   }
 }
 
@@ -842,7 +717,8 @@ heavy_reduce_kernel(const double* __restrict__ partials, int nu, double* __restr
 }
 
 // One CTA per heavy row of the batch: add the row's partials in a fixed order (8 warps take every
-// 8th entry, then the 8 sums are added in warp order), solve block fb, write the new factors and d_f.
+// 8th entry, then the 8 sums are added in warp order) while all threads form S.x of the block;
+// warp 0 then runs the 16-step recurrence; the new factors and d_f go to HBM.
 // override_count > 0: the row's partials are partials[0 .. override_count) (level-2 groups).
 template <int LD, bool USER>
 __global__ void __launch_bounds__(kBlkThreads)
@@ -851,12 +727,15 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int u0, int fb, const double
   __shared__ double x_s[LD];
   __shared__ double Gs[256];
   __shared__ double Pt[16];
-  __shared__ double delta_s[16];
+  __shared__ double Tt[16];
+  __shared__ double tpart[16][16];
   __shared__ double wsum[kBlkWarps][kPartLen];
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   const int h = h0 + blockIdx.x;
   const int row = hu.hrow_id[h];
   const int grow = a.row_base + row;
+  const int f0 = fb * kFB;
+  const double g = USER ? 1.0 : a.Wi[grow];
   double* xrow = a.X + (size_t)grow * LD;
   for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
   const int ufirst = override_count > 0 ? 0 : hu.hrow_unit0[h] - u0;
@@ -876,25 +755,63 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int u0, int fb, const double
       if (lane + 32 * t < kPartLen) wsum[warp][lane + 32 * t] = acc[t];
   }
   __syncthreads();
-  if (tid < kPartLen) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kBlkWarps; w++) s += wsum[w][tid];
-    scatter_partial(tid, s, Gs, Pt);
+  {   // S.x: thread = (factor, 1/16th of the k range); S symmetric -> unit stride over the factor
+    constexpr int kPer = LD / 16;
+    const int tf = tid & 15, part = tid >> 4;
+    const double* __restrict__ Sc = a.S + (size_t)(part * kPer) * LD + f0 + tf;
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < kPer; k += 2) {
+      t0 += x_s[part * kPer + k] * __ldg(Sc + (size_t)k * LD);
+      if (kPer > 1) t1 += x_s[part * kPer + k + 1] * __ldg(Sc + (size_t)(k + 1) * LD);
+    }
+    tpart[part][tf] = t0 + t1;
   }
-  __syncthreads();
-  if (tid < 32) {
-    const double g = USER ? 1.0 : a.Wi[grow];
-    double pt[16];
+  if (tid < kPartLen) {
+    double sum = 0.0;
 #pragma unroll
-    for (int e = 0; e < 16; e++) pt[e] = tid == 0 ? Pt[e] : 0.0;
-    solve_block<LD>(x_s, Gs, pt, delta_s, a.S, fb * kFB, a.K, g, a.reg);
+    for (int w = 0; w < kBlkWarps; w++) sum += wsum[w][tid];
+    if (tid < 192) {   // H = G + g S_BB
+      const int t = tid >> 6, l = (tid & 63) >> 1, ii = tid & 1;
+      int rw = l >> 2, cl = 2 * (l & 3) + ii;
+      if (t >= 1) rw += 8;
+      if (t == 2) cl += 8;
+      sum += g * __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
+      Gs[rw * 16 + cl] = sum;
+      if (t == 1) Gs[cl * 16 + rw] = sum;
+    } else {
+      Pt[tid - 192] = sum;
+    }
   }
   __syncthreads();
   if (tid < 16) {
-    delta[(size_t)h * 16 + tid] = delta_s[tid];
-    const int k = fb * kFB + tid;
-    if (k < a.K) xrow[k] = x_s[k];
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) sum += tpart[q][tid];
+    Tt[tid] = sum;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int ff = lane & 15;
+    double hcol[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) hcol[k] = Gs[k * 16 + ff];
+    const double hff = Gs[ff * 16 + ff];
+    const double xf = x_s[f0 + ff];
+    double numer = Pt[ff] - g * Tt[ff] + xf * hff;
+    const double rden = 1.0 / (hff + a.reg);
+#pragma unroll
+    for (int sidx = 0; sidx < 16; sidx++) {
+      const double d = numer * rden - xf;
+      const double ds = __shfl_sync(kFullMask, d, sidx);
+      if (ff > sidx) numer -= ds * hcol[sidx];
+    }
+    const double xnew = numer * rden;
+    if (lane < 16) {
+      const bool livef = f0 + ff < a.K;
+      delta[(size_t)h * 16 + ff] = livef ? xnew - xf : 0.0;
+      if (livef) xrow[f0 + ff] = xnew;
+    }
   }
 }
 
