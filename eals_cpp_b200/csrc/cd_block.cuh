@@ -59,15 +59,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Stage factor block fb of the rows idx_s[0..n) into the tile; rows [n, n_pad) are zero-filled.
-template <int LD>
-__device__ __forceinline__ void stage_tile_async(unsigned char* tile, const int* idx_s, const double* __restrict__ Y,
-                                                 int n, int n_pad, int fb, int tid, int nthreads) {
-  for (int q = tid; q < n_pad * 8; q += nthreads) {
-    const int r = q >> 3, c = q & 7;
+// Stage factor block fb of n gathered rows into the tile; rows [n, n_pad) are zero-filled.  The source
+// comes from a table of row base pointers (rowp_s[r] = &Y[idx[r]][0]) built once per row: per 16-byte
+// chunk one LDS.64, one add and the cp.async.  Thread t always copies chunk column t & 7 of rows
+// (t >> 3), (t >> 3) + nthreads/8, ...  (r01e: the index arithmetic of the version above was 16.5 % of
+// the team kernel's instructions.)
+__device__ __forceinline__ void stage_tile_rows(unsigned char* tile, const double* const* rowp_s, int n, int n_pad,
+                                                int fb, int tid, int nthreads) {
+  const int c = tid & 7;
+  const uint32_t col_bytes = (uint32_t)(fb * (kFB * 8) + c * 16);
+  for (int r = tid >> 3; r < n_pad; r += nthreads >> 3) {
     const bool live = r < n;
-    const double* src = live ? Y + (size_t)idx_s[r] * LD + fb * kFB + c * 2 : Y;
-    cp_async16(tile + tile_chunk_off(r, c), src, live ? 16 : 0);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(rowp_s[live ? r : 0]) + col_bytes;
+    cp_async16(tile + (uint32_t)(r * 128) + (uint32_t)(((c ^ r) & 7) << 4), src, live ? 16 : 0);
   }
 }
 
@@ -109,7 +113,7 @@ struct WarpBlockSmem {
   static constexpr size_t kS = kSInSmem ? (size_t)LD * LD * 8 : 0;
   static constexpr size_t kTile = (size_t)kRows * 128;
   // tile | idx | c | z | x | Gs[256] | Pt[16] | delta[16]
-  static constexpr size_t kBytesPerWarp = kTile + (size_t)kRows * (4 + 8 + 8) + (size_t)LD * 8 + (256 + 16 + 16) * 8;
+  static constexpr size_t kBytesPerWarp = kTile + (size_t)kRows * (8 + 8 + 8) + (size_t)LD * 8 + (256 + 16 + 16) * 8;
 };
 
 // Gram + right-hand-side fragments of tile rows [0, r1): frag[0..5] as gram_fragments, frag[6..7] =
@@ -156,8 +160,8 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 
   unsigned char* base = smem + Sm::kS + (size_t)warp * Sm::kBytesPerWarp;
   unsigned char* tile = base;
-  int* idx_s = reinterpret_cast<int*>(base + Sm::kTile);
-  double* c_s = reinterpret_cast<double*>(base + Sm::kTile + (size_t)Sm::kRows * 4);
+  const double** rowp_s = reinterpret_cast<const double**>(base + Sm::kTile);
+  double* c_s = reinterpret_cast<double*>(base + Sm::kTile + (size_t)Sm::kRows * 8);
   double* z_s = c_s + Sm::kRows;
   double* x_s = z_s + Sm::kRows;
   double* Gs = x_s + LD;
@@ -185,7 +189,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
       pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
       if (j < n) {
         const int id = a.idx[p0 + j];
-        idx_s[j] = id;
+        rowp_s[j] = a.Y + (size_t)id * LD;
         const double w = a.val ? a.val[p0 + j] : 1.0;
         wr[m] = w * w;
         cw[m] = w - (USER ? a.Wi[id] : wi_row);
@@ -199,7 +203,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 
     if (!a.use_cache) {   // prediction cache from scratch: p_j = <x, y_j>
       for (int fb = 0; fb < nblocks; fb++) {
-        stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, lane, 32);
+        stage_tile_rows(tile, rowp_s, n, n_pad, fb, lane, 32);
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
@@ -219,7 +223,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
       }
     }
 
-    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, 0, lane, 32);
+    stage_tile_rows(tile, rowp_s, n, n_pad, 0, lane, 32);
     cp_async_commit();
     for (int fb = 0; fb < nblocks; fb++) {
       const int f0 = fb * kFB;
@@ -314,7 +318,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
       }
       __syncwarp();
       if (fb + 1 < nblocks) {
-        stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb + 1, lane, 32);
+        stage_tile_rows(tile, rowp_s, n, n_pad, fb + 1, lane, 32);
         cp_async_commit();
       }
     }
@@ -346,7 +350,7 @@ struct RowBlockSmem {
   static constexpr int kT = TW * 32;                         // threads per CTA (team of TW warps)
   static constexpr int kRows = kT * MW;
   static constexpr size_t kTile = (size_t)kRows * 128;
-  static constexpr size_t kIdx = (size_t)kRows * 4;
+  static constexpr size_t kIdx = (size_t)kRows * 8;           // row base pointers
   static constexpr size_t kCZ = (size_t)kRows * 16;           // c and z
   static constexpr size_t kX = (size_t)LD * 8;
   static constexpr size_t kSlots = (size_t)TW * kPartLen * 8;
@@ -363,7 +367,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   constexpr int kParts = kT / 16;                            // S.x: threads = (factor, part of the k range)
   static_assert(kPartLen + 16 <= kT || TW < 8, "reduction threads");
   unsigned char* tile = smem;
-  int* idx_s = reinterpret_cast<int*>(smem + Sm::kTile);
+  const double** rowp_s = reinterpret_cast<const double**>(smem + Sm::kTile);
   double* c_s = reinterpret_cast<double*>(smem + Sm::kTile + Sm::kIdx);
   double* z_s = c_s + Sm::kRows;
   double* x_s = z_s + Sm::kRows;
@@ -392,7 +396,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
     pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
     if (j < n) {
       const int id = a.idx[p0 + j];
-      idx_s[j] = id;
+      rowp_s[j] = a.Y + (size_t)id * LD;
       const double w = a.val ? a.val[p0 + j] : 1.0;
       wr[m] = w * w;
       cw[m] = w - (USER ? a.Wi[id] : wi_row);
@@ -408,7 +412,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
 
   // Pass 1: prediction cache p_j = <x, y_j> (skipped when the symmetric cache is valid)
   for (int fb = 0; fb < (a.use_cache ? 0 : nblocks); fb++) {
-    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kT);
+    stage_tile_rows(tile, rowp_s, n, n_pad, fb, tid, kT);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -431,7 +435,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   const int w_r1 = min((warp + 1) * 32 * MW, n_pad);
   const int tf = tid & 15, tpart_id = tid >> 4;          // S.x: factor and 1/16th of the k range
   constexpr int kPer = LD / kParts;                       // k's per thread
-  stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, 0, tid, kT);
+  stage_tile_rows(tile, rowp_s, n, n_pad, 0, tid, kT);
   cp_async_commit();
   for (int fb = 0; fb < nblocks; fb++) {
     const int f0 = fb * kFB;
@@ -538,7 +542,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
     }
     __syncthreads();
     if (fb + 1 < nblocks) {
-      stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb + 1, tid, kT);
+      stage_tile_rows(tile, rowp_s, n, n_pad, fb + 1, tid, kT);
       cp_async_commit();
     }
   }
@@ -603,7 +607,7 @@ heavy_pred_kernel(CdSide a, HeavyUnits hu, int u0, double* __restrict__ pred) {
 
 struct HeavySmem {
   static constexpr size_t kTile = (size_t)kSlab * 128;       // x2: previous block (cache update) + this block
-  static constexpr size_t kIdx = (size_t)kSlab * 4;
+  static constexpr size_t kIdx = (size_t)kSlab * 8;          // row base pointers
   static constexpr size_t kCZ = (size_t)kSlab * 16;
   // the per-warp reduction slots (8 x 208 doubles) reuse the previous-block tile once it is consumed
   static constexpr size_t kBytes = 2 * kTile + kIdx + kCZ + 16 * 8;
@@ -621,7 +625,7 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* tile_prev = smem;
   unsigned char* tile = smem + HeavySmem::kTile;
-  int* idx_s = reinterpret_cast<int*>(smem + 2 * HeavySmem::kTile);
+  const double** rowp_s = reinterpret_cast<const double**>(smem + 2 * HeavySmem::kTile);
   double* c_s = reinterpret_cast<double*>(smem + 2 * HeavySmem::kTile + HeavySmem::kIdx);
   double* z_s = c_s + kSlab;
   double* delta_s = z_s + kSlab;
@@ -640,7 +644,7 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   double pr = 0.0, cw = 0.0, wr = 0.0;
   if (tid < n) {
     const int id = a.idx[off + tid];
-    idx_s[tid] = id;
+    rowp_s[tid] = a.Y + (size_t)id * LD;
     const double w = a.val ? a.val[off + tid] : 1.0;
     wr = w * w;
     cw = w - (USER ? a.Wi[id] : wi_row);
@@ -651,11 +655,11 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   __syncthreads();
 
   if (fb > 0) {
-    stage_tile_async<LD>(tile_prev, idx_s, a.Y, n, n_pad, fb - 1, tid, kBlkThreads);
+    stage_tile_rows(tile_prev, rowp_s, n, n_pad, fb - 1, tid, kBlkThreads);
     cp_async_commit();
   }
   if (fb < nblocks) {
-    stage_tile_async<LD>(tile, idx_s, a.Y, n, n_pad, fb, tid, kBlkThreads);
+    stage_tile_rows(tile, rowp_s, n, n_pad, fb, tid, kBlkThreads);
     cp_async_commit();
   }
   if (fb > 0) {
