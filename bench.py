@@ -354,17 +354,22 @@ def main():
         sm_host = SparseMat(M, N, *[k.numpy() for k in keep])
         own_u = int(sm.row_ptr[ue] - sm.row_ptr[ub]); own_i = int(sm.col_ptr[ie] - sm.col_ptr[ib])
         h2d = (own_u + own_i) * 4 + (ue - ub + 1 + ie - ib + 1) * 8      # what the library uploads per step
-        times = []
+        times, parts = [], []
         for it in range(1 + args.e2e_steps):
             barrier()
             t0 = time.perf_counter()
             fals.setTrain(sm_host)          # H2D of the CSR + CSC slices, bucketing
+            torch.cuda.synchronize(); t1 = time.perf_counter()
             epoch()
+            torch.cuda.synchronize(); t2 = time.perf_counter()
             _ = fals.loss()                 # D2H of the step's result
             barrier()
+            t3 = time.perf_counter()
             if it > 0:
-                times.append(time.perf_counter() - t0)
+                times.append(t3 - t0)
+                parts.append((t1 - t0, t2 - t1, t3 - t2))
         t_e2e = float(np.mean(times))
+        e2e_parts = dict(zip(("set_train_s", "epoch_s", "loss_s"), np.mean(np.asarray(parts), axis=0).tolist()))
         if world > 1:
             t = torch.tensor([t_e2e, float(h2d)], device=f"cuda:{local_rank}", dtype=torch.float64)
             tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -372,7 +377,8 @@ def main():
             t_e2e, h2d = float(tmax[0].item()), int(t[1].item())
         e2e = {"value": 2.0 * nnz * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 32 * world, "s_per_step": t_e2e, "steps": args.e2e_steps,
-               "what": "setTrain(host pinned CSR+CSC) + update_user + update_item + loss() per step"}
+               "what": "setTrain(host pinned CSR+CSC) + update_user + update_item + loss() per step",
+               "breakdown": e2e_parts}
         del keep, sm_host
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------

@@ -10,6 +10,7 @@
 #include "../../include/eals_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -51,11 +52,39 @@ int fail(int code, const char* fmt, ...) {
     if (r_ != EALS_OK) return r_; \
   } while (0)
 
+// EALS_VERBOSE=1: wall-clock of the setup stages on stderr.
+struct StageTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  StageTimer() : on(getenv("EALS_VERBOSE") && getenv("EALS_VERBOSE")[0] == '1'), t(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[eals] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 template <typename T>
 int dev_alloc(T** p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
   CU(cudaMalloc((void**)p, n * sizeof(T)));
+  return EALS_OK;
+}
+
+// Grow-only device buffer: reallocated only when the request exceeds the capacity, so that replacing
+// the train matrix by one of the same shape (setTrain) does not free and re-allocate gigabytes.
+template <typename T>
+int dev_reserve(T** p, size_t* cap, size_t n) {
+  if (n == 0) n = 1;
+  if (*p && n <= *cap) return EALS_OK;
+  cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CU(cudaMalloc((void**)p, n * sizeof(T)));
+  *cap = n;
   return EALS_OK;
 }
 
@@ -94,6 +123,10 @@ struct Side {
   std::vector<HeavyBatch> batches;
   double* pred = nullptr;             // prediction cache of the heavy rows (compact)
   double* delta = nullptr;            // [n_hrows][16] factor changes of the current block
+  // capacities (elements) of the device arrays above, see dev_reserve
+  size_t cap_ptr = 0, cap_idx = 0, cap_val = 0, cap_order = 0, cap_unit_row = 0, cap_unit_hrow = 0, cap_unit_cnt = 0,
+         cap_unit_off = 0, cap_unit_poff = 0, cap_hrow_id = 0, cap_hrow_unit0 = 0, cap_hrow_units = 0, cap_pred = 0,
+         cap_delta = 0;
   std::vector<int64_t> h_ptr;         // host copy of ptr (rebased to 0)
 };
 
@@ -127,6 +160,8 @@ struct eals_model {
   // symmetric prediction cache (single-rank models only)
   double* pcache = nullptr;      // [nnz] in CSR order
   uint32_t* csc2csr = nullptr;   // CSC position -> CSR position
+  size_t cap_pcache = 0, cap_csc2csr = 0;
+  bool pcache_on = false;        // structures built for the current matrix
   bool pcache_valid = false;
   int sweeps_since_fresh = 0;
   int pred_refresh_every = 0;    // EALS_PRED_REFRESH_EVERY: recompute the cache from scratch every n sweeps (0 = never)
@@ -167,16 +202,20 @@ int copy_in(T* dst, const T* src, size_t n, int space, cudaStream_t st) {
   return EALS_OK;
 }
 
+// One warp per row (grid-stride): every index in range and strictly larger than its predecessor.
 __global__ void check_sorted_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                     int rows, int limit, int* __restrict__ bad) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  int prev = -1;
-  for (int64_t p = ptr[r]; p < ptr[r + 1]; p++) {
-    const int c = idx[p];
-    if (c <= prev || c >= limit) { atomicExch(bad, 1); return; }
-    prev = c;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  bool ok = true;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
+    const int64_t p0 = ptr[r], p1 = ptr[r + 1];
+    for (int64_t p = p0 + lane; p < p1; p += 32) {
+      const int c = idx[p];
+      ok &= c >= 0 && c < limit && (p == p0 || idx[p - 1] < c);
+    }
   }
+  if (!ok) atomicExch(bad, 1);
 }
 
 int ensure_partials(eals_model* m, size_t n);
@@ -208,14 +247,15 @@ __global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz
 
 // (Re)build the symmetric prediction cache structures after the matrix changed.
 int build_pred_cache(eals_model* m) {
-  cudaFree(m->pcache); cudaFree(m->csc2csr);
-  m->pcache = nullptr; m->csc2csr = nullptr; m->pcache_valid = false;
+  StageTimer tm;
+  m->pcache_valid = false;
+  m->pcache_on = false;
   const bool single_rank = m->ub == 0 && m->ue == m->M && m->ib == 0 && m->ie == m->N;
   const int64_t nnz = m->users.nnz;
   const char* off = getenv("EALS_NO_PRED_CACHE");
   if (!single_rank || nnz == 0 || nnz >= 0xffffffffLL || nnz != m->items.nnz || (off && off[0] == '1')) return EALS_OK;
-  OK(dev_alloc(&m->pcache, (size_t)nnz));
-  OK(dev_alloc(&m->csc2csr, (size_t)nnz));
+  OK(dev_reserve(&m->pcache, &m->cap_pcache, (size_t)nnz));
+  OK(dev_reserve(&m->csc2csr, &m->cap_csc2csr, (size_t)nnz));
   const unsigned grid = (unsigned)((nnz + 255) / 256);
   build_csc2csr_kernel<<<grid, 256, 0, m->stream>>>(m->items.ptr, m->items.idx, m->N, m->users.ptr, m->users.idx, nnz, m->csc2csr);
   OK(check_launch(m));
@@ -229,6 +269,8 @@ int build_pred_cache(eals_model* m) {
   CU(cudaStreamSynchronize(m->stream));
   cudaFree(bad);
   if (h_bad) return fail(EALS_ERR_ARG, "the CSR and CSC arrays do not describe the same matrix");
+  tm.lap("pred cache: csc->csr map");
+  m->pcache_on = true;
   if (const char* e = getenv("EALS_PRED_REFRESH_EVERY")) m->pred_refresh_every = atoi(e);
   return EALS_OK;
 }
@@ -236,7 +278,7 @@ int build_pred_cache(eals_model* m) {
 // Upload the owned slice [begin, end) of one orientation of the matrix and bucket its rows.
 int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int space,
                const int64_t* ptr_full, const int32_t* idx_full, const double* val_full) {
-  free_side(s);
+  StageTimer tm;
   s.rows = end - begin;
   s.row_base = begin;
   s.h_ptr.assign((size_t)s.rows + 1, 0);
@@ -253,22 +295,28 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     if (s.h_ptr[r + 1] < s.h_ptr[r] || s.h_ptr[r + 1] - s.h_ptr[r] > other_dim)
       return fail(EALS_ERR_ARG, "offsets not monotone / row longer than the other dimension at row %d", begin + r);
   s.nnz = s.h_ptr[s.rows];
+  tm.lap("side: offsets to host+check");
 
-  OK(dev_alloc(&s.ptr, (size_t)s.rows + 1));
-  OK(dev_alloc(&s.idx, (size_t)s.nnz));
+  OK(dev_reserve(&s.ptr, &s.cap_ptr, (size_t)s.rows + 1));
+  OK(dev_reserve(&s.idx, &s.cap_idx, (size_t)s.nnz));
   CU(cudaMemcpyAsync(s.ptr, s.h_ptr.data(), sizeof(int64_t) * (s.rows + 1), cudaMemcpyHostToDevice, m->stream));
   OK(copy_in(s.idx, idx_full + base, (size_t)s.nnz, space, m->stream));
   if (val_full) {
-    OK(dev_alloc(&s.val, (size_t)s.nnz));
+    OK(dev_reserve(&s.val, &s.cap_val, (size_t)s.nnz));
     OK(copy_in(s.val, val_full + base, (size_t)s.nnz, space, m->stream));
+  } else if (s.val) {
+    cudaFree(s.val);
+    s.val = nullptr;
+    s.cap_val = 0;
   }
 
+  tm.lap("side: alloc + copy indices");
   // indices must ascend strictly inside a row and stay in range (main.cpp:198-205 order)
   if (s.rows > 0) {
     int* bad;
     OK(dev_alloc(&bad, 1));
     CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
-    check_sorted_kernel<<<(s.rows + 255) / 256, 256, 0, m->stream>>>(s.ptr, s.idx, s.rows, other_dim, bad);
+    check_sorted_kernel<<<std::min((s.rows + 7) / 8, 64 * m->sm_count), 256, 0, m->stream>>>(s.ptr, s.idx, s.rows, other_dim, bad);
     OK(check_launch(m));
     int h_bad = 0;
     CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -277,28 +325,37 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     if (h_bad) return fail(EALS_ERR_ARG, "indices inside a row must be strictly ascending and in range");
   }
 
+  tm.lap("side: validate sorted");
   // counting sort of the rows into length buckets
   std::vector<int32_t> order((size_t)std::max(s.rows, 1));
   int count[kNumBuckets] = {0};
-  auto bucket_of = [](int64_t n) {
-    int b = 0;
+  constexpr int kLut = kBucketMax[kHeavyBucket - 1] + 2;        // lengths 0..512 by table, longer = heavy
+  uint8_t lut[kLut];
+  for (int n = 0, b = 0; n < kLut; n++) {
     while (n > kBucketMax[b]) b++;
-    return b;
-  };
-  for (int r = 0; r < s.rows; r++) count[bucket_of(s.h_ptr[r + 1] - s.h_ptr[r])]++;
+    lut[n] = (uint8_t)b;
+  }
+  std::vector<uint8_t> bucket((size_t)std::max(s.rows, 1));
+  for (int r = 0; r < s.rows; r++) {
+    const int64_t n = s.h_ptr[r + 1] - s.h_ptr[r];
+    const uint8_t b = lut[std::min<int64_t>(n, kLut - 1)];
+    bucket[r] = b;
+    count[b]++;
+  }
   s.first[0] = 0;
   for (int b = 0; b < kNumBuckets; b++) s.first[b + 1] = s.first[b] + count[b];
   int fill[kNumBuckets];
   for (int b = 0; b < kNumBuckets; b++) fill[b] = s.first[b];
-  for (int r = 0; r < s.rows; r++) order[fill[bucket_of(s.h_ptr[r + 1] - s.h_ptr[r])]++] = r;
+  for (int r = 0; r < s.rows; r++) order[fill[bucket[r]]++] = r;
   // long rows: longest first, so the tail of the launch is made of the cheapest rows
   std::stable_sort(order.begin() + s.first[kHeavyBucket], order.begin() + s.first[kHeavyBucket + 1],
                    [&](int a, int b) {
                      return s.h_ptr[a + 1] - s.h_ptr[a] > s.h_ptr[b + 1] - s.h_ptr[b];
                    });
-  OK(dev_alloc(&s.order, order.size()));
+  OK(dev_reserve(&s.order, &s.cap_order, order.size()));
   CU(cudaMemcpyAsync(s.order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, m->stream));
 
+  tm.lap("side: bucket rows");
   // heavy rows -> slabs ("units") of kSlab nonzeros and batches of rows
   {
     const int hb = s.first[kHeavyBucket], he = s.first[kHeavyBucket + 1];
@@ -306,6 +363,13 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     std::vector<int32_t> unit_row, unit_hrow, unit_cnt, hrow_id;
     std::vector<int64_t> unit_off, unit_poff;
     s.h_hrow_unit0.clear(); s.h_hrow_units.clear(); s.batches.clear(); s.h_row_to_hrow.clear();
+    {
+      int64_t hn = 0;
+      for (int h = 0; h < s.n_hrows; h++) { const int r = order[hb + h]; hn += s.h_ptr[r + 1] - s.h_ptr[r]; }
+      const size_t est = (size_t)(hn / eals::kSlab) + (size_t)s.n_hrows + 1;
+      unit_row.reserve(est); unit_hrow.reserve(est); unit_cnt.reserve(est); unit_off.reserve(est); unit_poff.reserve(est);
+      hrow_id.reserve((size_t)s.n_hrows); s.h_hrow_unit0.reserve((size_t)s.n_hrows); s.h_hrow_units.reserve((size_t)s.n_hrows);
+    }
     int64_t poff = 0, batch_nnz = 0;
     int64_t batch_limit = kDefaultBatchNnz;
     if (const char* e = getenv("EALS_HEAVY_BATCH_NNZ")) batch_limit = std::max<int64_t>(atoll(e), 1);
@@ -343,25 +407,28 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     s.heavy_nnz = poff;
     s.max_batch_units = 0;
     for (const auto& b : s.batches) s.max_batch_units = std::max(s.max_batch_units, b.u1 - b.u0);
-    auto up32 = [&](int32_t** d, const std::vector<int32_t>& v) -> int {
-      OK(dev_alloc(d, v.size()));
+    auto up32 = [&](int32_t** d, size_t* cap, const std::vector<int32_t>& v) -> int {
+      OK(dev_reserve(d, cap, v.size()));
       if (!v.empty()) CU(cudaMemcpyAsync(*d, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, m->stream));
       return EALS_OK;
     };
-    auto up64 = [&](int64_t** d, const std::vector<int64_t>& v) -> int {
-      OK(dev_alloc(d, v.size()));
+    auto up64 = [&](int64_t** d, size_t* cap, const std::vector<int64_t>& v) -> int {
+      OK(dev_reserve(d, cap, v.size()));
       if (!v.empty()) CU(cudaMemcpyAsync(*d, v.data(), sizeof(int64_t) * v.size(), cudaMemcpyHostToDevice, m->stream));
       return EALS_OK;
     };
-    OK(up32(&s.unit_row, unit_row)); OK(up32(&s.unit_hrow, unit_hrow)); OK(up32(&s.unit_cnt, unit_cnt));
-    OK(up64(&s.unit_off, unit_off)); OK(up64(&s.unit_poff, unit_poff));
-    OK(up32(&s.hrow_id, hrow_id)); OK(up32(&s.hrow_unit0, s.h_hrow_unit0)); OK(up32(&s.hrow_units, s.h_hrow_units));
-    OK(dev_alloc(&s.pred, (size_t)s.heavy_nnz));
-    OK(dev_alloc(&s.delta, (size_t)s.n_hrows * 16));
+    OK(up32(&s.unit_row, &s.cap_unit_row, unit_row)); OK(up32(&s.unit_hrow, &s.cap_unit_hrow, unit_hrow));
+    OK(up32(&s.unit_cnt, &s.cap_unit_cnt, unit_cnt));
+    OK(up64(&s.unit_off, &s.cap_unit_off, unit_off)); OK(up64(&s.unit_poff, &s.cap_unit_poff, unit_poff));
+    OK(up32(&s.hrow_id, &s.cap_hrow_id, hrow_id)); OK(up32(&s.hrow_unit0, &s.cap_hrow_unit0, s.h_hrow_unit0));
+    OK(up32(&s.hrow_units, &s.cap_hrow_units, s.h_hrow_units));
+    OK(dev_reserve(&s.pred, &s.cap_pred, (size_t)s.heavy_nnz));
+    OK(dev_reserve(&s.delta, &s.cap_delta, (size_t)s.n_hrows * 16));
     CU(cudaStreamSynchronize(m->stream));   // the host vectors above go out of scope
     // size the partials scratch now: a reallocation in the middle of a sweep would synchronise
     OK(ensure_partials(m, (size_t)(s.max_batch_units + (s.max_batch_units + 31) / 32 + 2) * eals::kPartLen));
   }
+  tm.lap("side: heavy units + upload");
   CU(cudaStreamSynchronize(m->stream));
   return EALS_OK;
 }
@@ -600,7 +667,7 @@ int sweep(eals_model* m, bool user, int only_row) {
   a.pcache = nullptr; a.perm = nullptr; a.use_cache = 0;
   if (only_row >= 0) {
     m->pcache_valid = false;           // a single-row update changes factors behind the cache's back
-  } else if (m->pcache) {
+  } else if (m->pcache_on) {
     if (m->pred_refresh_every > 0 && m->sweeps_since_fresh >= m->pred_refresh_every) m->pcache_valid = false;
     a.pcache = m->pcache;
     a.perm = user ? nullptr : m->csc2csr;
@@ -721,7 +788,14 @@ int loss_terms(eals_model* m, double terms[4]) {
   a.ptr = s.ptr; a.idx = s.idx; a.val = s.val;
   a.X = m->U; a.Y = m->V; a.Wi = m->Wi; a.row_base = s.row_base;
   int np = 0;
-  DISPATCH_LD(m->LD, OK(launch_loss_rows<LD>(m, a, s, &np)));
+  if (m->pcache_on && m->pcache_valid) {   // every prediction is already cached: stream it, no gather
+    np = 8 * m->sm_count;
+    OK(ensure_partials(m, (size_t)np));
+    eals::loss_cached_kernel<<<np, eals::kLossThreads, 0, m->stream>>>(s.idx, s.val, m->pcache, m->Wi, s.nnz, m->partials);
+    OK(check_launch(m));
+  } else {
+    DISPATCH_LD(m->LD, OK(launch_loss_rows<LD>(m, a, s, &np)));
+  }
   eals::sum_partials_kernel<<<1, 256, 0, m->stream>>>(m->partials, np, m->terms + 0, 0);
   OK(check_launch(m));
   const int g = 4 * m->sm_count;

@@ -6,8 +6,8 @@
 //  and removes the old-factor clone the reference keeps per iteration (:119,137).
 //
 // Two stages so the result is run-to-run deterministic: every CTA reduces a contiguous slab of
-// rows into its own TB x TB partial (register-tiled, operands staged in shared memory), then a
-// second kernel adds the partials in slab order and mirrors the off-diagonal blocks.
+// rows into its own TB x TB partial on the fp64 tensor cores (operands staged in shared memory), then
+// a second kernel adds the partials in slab order and mirrors the off-diagonal blocks.
 #pragma once
 
 #include "common.cuh"
@@ -26,14 +26,25 @@ struct GramCfg {
 };
 
 // partials layout: [pair][slab][TB*TB]
+//
+// Tensor-core version (fp64 mma.sync.m8n8k4): the CTA's 8 warps tile the TB x TB output block as
+// 8 x 8 DMMA tiles (warp w owns tile rows [w*TB/8 ...) — for TB = 128 two tile rows, i.e. 2 x 16 tiles
+// would be 64 accumulator registers; instead each warp owns a (TB/8) x ... strip, see below); rows of X
+// are staged 16 at a time through shared memory (A = X^T chunk, B = diag(w) X chunk).
 template <int LD>
 __global__ void __launch_bounds__(kGramThreads)
 gram_partial_kernel(const double* __restrict__ X, const double* __restrict__ w, int r0, int r1,
                     double* __restrict__ partials) {
   using C = GramCfg<LD>;
-  __shared__ double As[kGramChunk][C::TB];
-  __shared__ double Bs[kGramChunk][C::TB];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  constexpr int TB = C::TB;
+  constexpr int NT = TB / 8;                 // 8 x 8 tiles per dimension of the output block
+  constexpr int TPW = (NT * NT + 7) / 8;     // tiles per warp (TB = 128: 32, 64: 8, 32: 2, 16: 1)
+  // staged rows: As[r][c] = X[row][bi*TB + c], Bs[r][c] = w[row] * X[row][bj*TB + c]; stride TB + 4
+  // doubles keeps the 4-row x 8-column fragment reads on distinct banks
+  constexpr int ST = TB + 4;
+  __shared__ double As[kGramChunk][ST];
+  __shared__ double Bs[kGramChunk][ST];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int bi = 0, bj = 0;
   if (C::NB == 2) {  // pair 0 -> (0,0), 1 -> (1,0), 2 -> (1,1)
     bi = blockIdx.y >= 1;
@@ -44,45 +55,52 @@ gram_partial_kernel(const double* __restrict__ X, const double* __restrict__ w, 
   const int s0 = r0 + blockIdx.x * per;
   const int s1 = min(s0 + per, r1);
 
-  double acc[C::TT][C::TT];
+  double acc[TPW][2];
 #pragma unroll
-  for (int i = 0; i < C::TT; i++)
-#pragma unroll
-    for (int j = 0; j < C::TT; j++) acc[i][j] = 0.0;
+  for (int t = 0; t < TPW; t++) acc[t][0] = acc[t][1] = 0.0;
 
   for (int c0 = s0; c0 < s1; c0 += kGramChunk) {
-    for (int t = tid; t < kGramChunk * C::TB; t += kGramThreads) {
-      const int r = t / C::TB, c = t % C::TB;
+    for (int t = tid; t < kGramChunk * TB; t += kGramThreads) {
+      const int r = t / TB, c = t % TB;
       const int row = c0 + r;
       double a = 0.0, b = 0.0;
       if (row < s1) {
-        a = X[(size_t)row * LD + bi * C::TB + c];
-        b = X[(size_t)row * LD + bj * C::TB + c];
+        a = X[(size_t)row * LD + bi * TB + c];
+        b = X[(size_t)row * LD + bj * TB + c];
         if (w) b *= w[row];
       }
       As[r][c] = a;
       Bs[r][c] = b;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int r = 0; r < kGramChunk; r++) {
-      double av[C::TT], bv[C::TT];
 #pragma unroll
-      for (int i = 0; i < C::TT; i++) av[i] = As[r][ty + 16 * i];
+    for (int k0 = 0; k0 < kGramChunk; k0 += 4) {
 #pragma unroll
-      for (int j = 0; j < C::TT; j++) bv[j] = Bs[r][tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < C::TT; i++)
-#pragma unroll
-        for (int j = 0; j < C::TT; j++) acc[i][j] += av[i] * bv[j];
+      for (int t = 0; t < TPW; t++) {
+        const int tile = warp * TPW + t;
+        if (tile < NT * NT) {
+          const int ti = tile / NT, tj = tile % NT;
+          const double a = As[k0 + (lane & 3)][ti * 8 + (lane >> 2)];   // A[row = f][col = k]
+          const double b = Bs[k0 + (lane & 3)][tj * 8 + (lane >> 2)];   // B[row = k][col = f']
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(acc[t][0]), "+d"(acc[t][1])
+                       : "d"(a), "d"(b));
+        }
+      }
     }
     __syncthreads();
   }
-  double* out = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * C::TB * C::TB;
+  double* out = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TB * TB;
 #pragma unroll
-  for (int i = 0; i < C::TT; i++)
-#pragma unroll
-    for (int j = 0; j < C::TT; j++) out[(ty + 16 * i) * C::TB + tx + 16 * j] = acc[i][j];
+  for (int t = 0; t < TPW; t++) {
+    const int tile = warp * TPW + t;
+    if (tile < NT * NT) {
+      const int ti = tile / NT, tj = tile % NT;
+      const int rr = ti * 8 + (lane >> 2), cc = tj * 8 + 2 * (lane & 3);
+      out[rr * TB + cc] = acc[t][0];
+      out[rr * TB + cc + 1] = acc[t][1];
+    }
+  }
 }
 
 // S[f][k] = sum over slabs (ascending) of the partials; rows f >= K are not written.

@@ -85,6 +85,30 @@ loss_rows_kernel(LossSide a, const int32_t* __restrict__ order, int first, int c
   }
 }
 
+// Per-nonzero part from the symmetric prediction cache (CSR order): p = <u, v> is already there, so
+// the loss is one streaming pass over (index, cached prediction) plus the Wi gather.
+__global__ void __launch_bounds__(kLossThreads)
+loss_cached_kernel(const int32_t* __restrict__ idx, const double* __restrict__ val, const double* __restrict__ pcache,
+                   const double* __restrict__ Wi, int64_t nnz, double* __restrict__ partials) {
+  __shared__ double red[kLossThreads / 32];
+  double acc = 0.0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+    const double p = pcache[q];
+    const double r = val ? val[q] : 1.0;
+    const double d = r - p;
+    acc += r * (d * d) - __ldg(Wi + idx[q]) * (p * p);
+  }
+  acc = warp_sum(acc);
+  if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; w++) s += red[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
 // Sum of squares of rows [r0, r1) (DenseMat::squaredSum, DenseMat.cpp:86-92); padding is zero.
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const double* __restrict__ X, size_t begin, size_t end, double* __restrict__ partials) {

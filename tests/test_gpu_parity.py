@@ -112,6 +112,30 @@ def test_prediction_cache_modes_agree_with_oracle(mode, monkeypatch):
     assert np.abs(fals.V - port.V).max() < 1e-10
 
 
+def test_set_train_replaces_the_matrix_and_keeps_weights():
+    """setTrain (MF_fastALS.cpp:94-104): new matrix of the same shape, factors and Wi kept; device
+    buffers are reused, the prediction cache is rebuilt."""
+    from eals_cpp_b200.model import SparseMat
+    from oracle.bindings import PortModel
+    M, N, K = 700, 500, 32
+    rpA, ciA = random_csr(M, N, 15, seed=1)
+    rpB, ciB = random_csr(M, N, 22, seed=2, empty_frac=0.1)      # more nonzeros than A: buffers must grow
+    fals, port = _models(M, N, rpA, ciA, K)
+    fals.update_user(); fals.update_item()
+    for rp, ci in ((rpB, ciB), (rpA, ciA)):
+        fals.setTrain(SparseMat.from_csr(M, N, rp, ci))
+        port = PortModel(M, N, rp, ci, factors=K)
+        port.U[:], port.V[:], port.Wi[:] = fals.U, fals.V, fals.Wi
+        port.init_S()
+        for _ in range(2):
+            fals.update_user(); port.update_user()
+            fals.update_item(); port.update_item()
+        assert np.abs(fals.U - port.U).max() < 1e-10
+        assert np.abs(fals.V - port.V).max() < 1e-10
+        lg, lc = fals.loss(), port.loss()          # loss() streams the prediction cache here
+        assert abs(lg - lc) <= 1e-10 * abs(lc)
+
+
 def test_weighted_ratings_match_oracle():
     """Non-unit ratings: W is a copy of the rating values (MF_fastALS.cpp:75-82)."""
     M, N, K = 200, 150, 16
