@@ -874,16 +874,55 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
   eals::eval_gt_score_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->U, m->V, gt_dev, d_users, 0, n, K, LD, d_gts);
   OK(check_launch(m));
   const int item_tiles = (N + eals::kEvalTile - 1) / eals::kEvalTile;
+  // Count strictly larger scores chunk by chunk of items.  The reference gives (0,0,0) as soon as the
+  // count exceeds topK (MF_fastALS.cpp:633-634) and the total does not depend on the scan order, so a
+  // user whose count already exceeds topK after a chunk is decided and leaves the active list; only
+  // the users still in the race (the eventual hits and near-hits) are scored against the whole
+  // catalogue.  Chunks grow geometrically: 4096, 16384, ... items.
+  std::vector<int32_t> cnt((size_t)n, 0);
   {
-    const long long tiles = (long long)((n + eals::kEvalTile - 1) / eals::kEvalTile) * item_tiles;
-    if (tiles > 0x7fffffffLL) return fail(EALS_ERR_UNSUPPORTED, "evaluate: too many tiles");
-    eals::eval_tile_kernel<0><<<(unsigned)tiles, eals::kEvalThreads, 0, m->stream>>>(
-        m->U, m->V, d_users, 0, n, N, K, LD, d_gts, d_count, nullptr, nullptr, 0);
-    OK(check_launch(m));
+    std::vector<int32_t> active((size_t)n);
+    for (int s = 0; s < n; s++) active[s] = s;
+    int32_t* d_active = nullptr;
+    OK(dev_alloc(&d_active, (size_t)n));
+    std::vector<int32_t> cnt_a;
+    int64_t chunk = 4096;
+    if (const char* e = getenv("EALS_EVAL_FIRST_CHUNK")) chunk = std::max<int64_t>(64, atoll(e));
+    for (int64_t i0 = 0; i0 < N && !active.empty(); i0 += chunk, chunk *= 4) {
+      const int i1 = (int)std::min<int64_t>(N, i0 + chunk);
+      const int na = (int)active.size();
+      CU(cudaMemcpyAsync(d_active, active.data(), sizeof(int32_t) * na, cudaMemcpyHostToDevice, m->stream));
+      const long long utiles = (na + eals::kEvalTile - 1) / eals::kEvalTile;
+      const long long itiles = (i1 - (int)i0 + eals::kEvalTile - 1) / eals::kEvalTile;
+      // keep each launch below the grid limit: split the active list if needed
+      const long long max_ut = std::max<long long>(1, 0x7fffffffLL / itiles);
+      for (long long ut0 = 0; ut0 < utiles; ut0 += max_ut) {
+        const long long ut1 = std::min(utiles, ut0 + max_ut);
+        const int a0 = (int)(ut0 * eals::kEvalTile), a1 = (int)std::min<long long>(na, ut1 * eals::kEvalTile);
+        eals::eval_tile_kernel<0><<<(unsigned)((ut1 - ut0) * itiles), eals::kEvalThreads, 0, m->stream>>>(
+            m->U, m->V, d_users, d_active + a0, 0, a1 - a0, (int)i0, i1, K, LD, d_gts, d_count, nullptr, nullptr, 0);
+        OK(check_launch(m));
+      }
+      if (na == n) {   // first round: everything
+        CU(cudaMemcpyAsync(cnt.data(), d_count, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+      } else {         // later rounds: the (few) active slots only
+        OK(ensure_partials(m, (size_t)(na + 1) / 2 + 1));
+        int32_t* d_tmp = reinterpret_cast<int32_t*>(m->partials);
+        eals::gather_i32_kernel<<<(na + 255) / 256, 256, 0, m->stream>>>(d_count, d_active, na, d_tmp);
+        OK(check_launch(m));
+        cnt_a.resize((size_t)na);
+        CU(cudaMemcpyAsync(cnt_a.data(), d_tmp, sizeof(int32_t) * na, cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        for (int a = 0; a < na; a++) cnt[active[a]] = cnt_a[a];
+      }
+      size_t keep = 0;
+      for (int a = 0; a < na; a++)
+        if (cnt[active[a]] <= topk) active[keep++] = active[a];
+      active.resize(keep);
+    }
+    cudaFree(d_active);
   }
-  std::vector<int32_t> cnt((size_t)n);
-  CU(cudaMemcpyAsync(cnt.data(), d_count, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, m->stream));
-  CU(cudaStreamSynchronize(m->stream));
 
   std::vector<int> pos((size_t)n, -1);
   if (mode == EALS_EVAL_EXACT) {
@@ -903,14 +942,29 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
       OK(dev_alloc(&d_nt, 1));
       CU(cudaMemcpyAsync(d_su, surv_users.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, m->stream));
       unsigned long long cap = 1ull << 20, got = 0;
-      const long long tiles = (long long)((ns + eals::kEvalTile - 1) / eals::kEvalTile) * item_tiles;
+      // survivor tiles per launch bounded by the grid limit; `active` = identity so that the slot a
+      // sub-launch reports is the absolute survivor index
+      int32_t* d_iota = nullptr;
+      {
+        std::vector<int32_t> iota((size_t)ns);
+        for (int t = 0; t < ns; t++) iota[t] = t;
+        OK(dev_alloc(&d_iota, (size_t)ns));
+        CU(cudaMemcpyAsync(d_iota, iota.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+      }
+      const long long utiles = (ns + eals::kEvalTile - 1) / eals::kEvalTile;
+      const long long max_ut = std::max<long long>(1, 0x7fffffffLL / item_tiles);
       for (int attempt = 0; attempt < 2; attempt++) {
         cudaFree(d_tr);
         OK(dev_alloc(&d_tr, (size_t)cap));
         CU(cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), m->stream));
-        eals::eval_tile_kernel<1><<<(unsigned)tiles, eals::kEvalThreads, 0, m->stream>>>(
-            m->U, m->V, d_su, 0, ns, N, K, LD, nullptr, nullptr, d_tr, d_nt, cap);
-        OK(check_launch(m));
+        for (long long ut0 = 0; ut0 < utiles; ut0 += max_ut) {
+          const long long ut1 = std::min(utiles, ut0 + max_ut);
+          const int a0 = (int)(ut0 * eals::kEvalTile), a1 = (int)std::min<long long>(ns, ut1 * eals::kEvalTile);
+          eals::eval_tile_kernel<1><<<(unsigned)((ut1 - ut0) * item_tiles), eals::kEvalThreads, 0, m->stream>>>(
+              m->U, m->V, d_su, d_iota + a0, 0, a1 - a0, 0, N, K, LD, nullptr, nullptr, d_tr, d_nt, cap);
+          OK(check_launch(m));
+        }
         CU(cudaMemcpyAsync(&got, d_nt, sizeof(got), cudaMemcpyDeviceToHost, m->stream));
         CU(cudaStreamSynchronize(m->stream));
         if (got <= cap) break;
@@ -918,7 +972,7 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
       }
       std::vector<eals::EvalTriple> tr((size_t)got);
       if (got) CU(cudaMemcpy(tr.data(), d_tr, sizeof(eals::EvalTriple) * got, cudaMemcpyDeviceToHost));
-      cudaFree(d_su); cudaFree(d_nt); cudaFree(d_tr);
+      cudaFree(d_su); cudaFree(d_nt); cudaFree(d_tr); cudaFree(d_iota);
       std::sort(tr.begin(), tr.end(), [](const eals::EvalTriple& a, const eals::EvalTriple& b) {
         return a.slot != b.slot ? a.slot < b.slot : a.item < b.item;
       });

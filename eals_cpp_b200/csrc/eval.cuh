@@ -33,6 +33,13 @@ __global__ void eval_gt_score_kernel(const double* __restrict__ U, const double*
   out[s] = seq_dot(U + (size_t)u * LD, V + (size_t)gt[s] * LD, K);
 }
 
+// out[a] = src[index[a]]
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ index, int n,
+                                  int32_t* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n) out[a] = src[index[a]];
+}
+
 constexpr int kEvalTile = 64;     // users x items per CTA tile
 constexpr int kEvalThreads = 256; // 16 x 16 threads, 4 x 4 scores each
 constexpr int kEvalKC = 16;       // factor chunk staged per step
@@ -43,21 +50,23 @@ struct EvalTriple {
   int32_t key;
 };
 
-// MODE 0: count_larger[s] += #{ i : score(s,i) > gt_score[s] }.
+// MODE 0: count_larger[s] += #{ i in [item_begin, n_items) : score(s,i) > gt_score[s] }.
 // MODE 1: append (s, i, (int)score) for every (s,i) with (int)score != 0 to `triples`.
+// `active` (nullable): the a-th row of the launch is slot active[a]; n_slots = number of rows.
 template <int MODE>
 __global__ void __launch_bounds__(kEvalThreads)
 eval_tile_kernel(const double* __restrict__ U, const double* __restrict__ V,
-                 const int32_t* __restrict__ users, int u_begin, int n_slots, int n_items, int K, int LD,
+                 const int32_t* __restrict__ users, const int32_t* __restrict__ active, int u_begin, int n_slots,
+                 int item_begin, int n_items, int K, int LD,
                  const double* __restrict__ gt_score, int32_t* __restrict__ count_larger,
                  EvalTriple* __restrict__ triples, unsigned long long* __restrict__ n_triples,
                  unsigned long long cap_triples) {
   __shared__ double Us[kEvalKC][kEvalTile + 1];
   __shared__ double Vs[kEvalKC][kEvalTile + 1];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int item_tiles = (n_items + kEvalTile - 1) / kEvalTile;
+  const int item_tiles = (n_items - item_begin + kEvalTile - 1) / kEvalTile;
   const int ut = blockIdx.x / item_tiles, it = blockIdx.x % item_tiles;
-  const int s0 = ut * kEvalTile, i0 = it * kEvalTile;
+  const int s0 = ut * kEvalTile, i0 = item_begin + it * kEvalTile;
 
   double acc[4][4];
 #pragma unroll
@@ -71,8 +80,9 @@ eval_tile_kernel(const double* __restrict__ U, const double* __restrict__ V,
       const int r = t / kEvalKC, kk = t % kEvalKC;
       double uv = 0.0, vv = 0.0;
       if (k0 + kk < K) {
-        const int s = s0 + r;
-        if (s < n_slots) {
+        const int sa = s0 + r;
+        if (sa < n_slots) {
+          const int s = active ? active[sa] : sa;
           const int u = users ? users[s] : u_begin + s;
           uv = U[(size_t)u * LD + k0 + kk];
         }
@@ -100,8 +110,9 @@ eval_tile_kernel(const double* __restrict__ U, const double* __restrict__ V,
 
 #pragma unroll
   for (int a = 0; a < 4; a++) {
-    const int s = s0 + ty + 16 * a;
-    const bool live = s < n_slots;
+    const int sa = s0 + ty + 16 * a;
+    const bool live = sa < n_slots;
+    const int s = live ? (active ? active[sa] : sa) : 0;
     if (MODE == 0) {
       const double g = live ? gt_score[s] : 0.0;
       int c = 0;

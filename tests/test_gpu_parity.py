@@ -243,10 +243,14 @@ def port_predict(port, u, i):
     return acc
 
 
+@pytest.mark.parametrize("first_chunk", [None, "64"])
 @pytest.mark.parametrize("scale", [1.0, 40.0])
-def test_evaluate_matches_oracle_bug_for_bug(scale):
+def test_evaluate_matches_oracle_bug_for_bug(scale, first_chunk, monkeypatch):
     """scale=40 inflates the factors so that truncated scores are non-zero (and some negative):
-    exercises the heap replay beyond the all-zero-keys case."""
+    exercises the heap replay beyond the all-zero-keys case.  first_chunk=64 forces several rounds
+    of the chunked early-out scan (64, 256, ... items) on this small catalogue."""
+    if first_chunk:
+        monkeypatch.setenv("EALS_EVAL_FIRST_CHUNK", first_chunk)
     M, N, K, topK = 500, 333, 16, 10
     row_ptr, col_idx = random_csr(M, N, 12, seed=21)
     fals, port = _models(M, N, row_ptr, col_idx, K)
