@@ -322,7 +322,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
         cp_async_commit();
       }
     }
-    for (int k = lane; k < K; k += 32) xrow[k] = x_s[k];
+    for (int k = lane; k < K; k += 32) store_row_value(a, (size_t)grow * LD + k, x_s[k]);
     if (a.pcache) {
 #pragma unroll
       for (int m = 0; m < MAXM; m++) {
@@ -546,7 +546,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       cp_async_commit();
     }
   }
-  for (int k = tid; k < K; k += kT) xrow[k] = x_s[k];
+  for (int k = tid; k < K; k += kT) store_row_value(a, (size_t)grow * LD + k, x_s[k]);
   if (a.pcache) {
 #pragma unroll
     for (int m = 0; m < MW; m++) {
@@ -814,7 +814,7 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int u0, int fb, const double
     if (lane < 16) {
       const bool livef = f0 + ff < a.K;
       delta[(size_t)h * 16 + ff] = livef ? xnew - xf : 0.0;
-      if (livef) xrow[f0 + ff] = xnew;
+      if (livef) store_row_value(a, (size_t)grow * LD + f0 + ff, xnew);
     }
   }
 }

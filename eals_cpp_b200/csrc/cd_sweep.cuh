@@ -26,6 +26,15 @@
 
 namespace eals {
 
+// Replicas of the factor matrix being updated on the other GPUs of the box (CUDA IPC mappings of
+// their X buffers): a finished row is stored straight into every replica over NVLink, which fuses
+// the all-gather of the updated rows into the sweep.
+constexpr int kMaxPeers = 7;
+struct PeerSet {
+  double* x[kMaxPeers];
+  int n;
+};
+
 struct CdSide {
   const int64_t* ptr;   // [rows+1] offsets of the owned rows (first owned row at 0)
   const int32_t* idx;   // neighbour ids, ascending inside a row
@@ -44,7 +53,13 @@ struct CdSide {
   double* pcache;       // nullptr: no cache
   const uint32_t* perm;
   int use_cache;        // 1: pcache is valid on entry, read it instead of recomputing
+  PeerSet peers;        // other ranks' replicas of X (n = 0: none)
 };
+
+__device__ __forceinline__ void store_row_value(const CdSide& a, size_t off, double v) {
+  a.X[off] = v;
+  for (int p = 0; p < a.peers.n; p++) a.peers.x[p][off] = v;
+}
 
 __device__ __forceinline__ int64_t cache_pos(const CdSide& a, int64_t q) { return a.perm ? (int64_t)a.perm[q] : q; }
 
@@ -177,7 +192,7 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
       __syncwarp();
     }
   }
-  for (int k = lane; k < K; k += 32) xrow[k] = u_s[k];
+  for (int k = lane; k < K; k += 32) store_row_value(a, (size_t)grow * LD + k, u_s[k]);
   if (a.pcache) {
 #pragma unroll
     for (int m = 0; m < MAXM; m++)

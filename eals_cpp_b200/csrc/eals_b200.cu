@@ -157,6 +157,7 @@ struct eals_model {
   double acc_ms[T_COUNT] = {0};
   int64_t acc_calls[T_COUNT] = {0};
   bool factors_set = false;
+  eals::PeerSet peersU = {}, peersV = {};   // IPC mappings of the other ranks' U / V replicas
   // symmetric prediction cache (single-rank models only)
   double* pcache = nullptr;      // [nnz] in CSR order
   uint32_t* csc2csr = nullptr;   // CSC position -> CSR position
@@ -665,6 +666,7 @@ int sweep(eals_model* m, bool user, int only_row) {
   a.K = m->K;
   a.reg = m->p.reg;
   a.pcache = nullptr; a.perm = nullptr; a.use_cache = 0;
+  a.peers = user ? m->peersU : m->peersV;
   if (only_row >= 0) {
     m->pcache_valid = false;           // a single-row update changes factors behind the cache's back
   } else if (m->pcache_on) {
@@ -1023,6 +1025,7 @@ int eals_destroy(eals_model* m) {
   if (!m) return EALS_OK;
   cudaSetDevice(m->p.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  eals_ipc_detach(m);
   free_side(m->users);
   free_side(m->items);
   cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
@@ -1346,6 +1349,47 @@ int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own) {
   CU(cudaStreamSynchronize(m->stream));
   fold_timings(m);
   m->stream = restore_own ? m->own_stream : (cudaStream_t)cuda_stream;
+  return EALS_OK;
+}
+
+int eals_ipc_handle(eals_model* m, int32_t which, void* handle_out) {
+  if (!m || !handle_out) return fail(EALS_ERR_ARG, "null argument");
+  if (which != EALS_BUF_U && which != EALS_BUF_V) return fail(EALS_ERR_ARG, "only U and V can be shared");
+  static_assert(sizeof(cudaIpcMemHandle_t) == EALS_IPC_HANDLE_BYTES, "IPC handle size");
+  CU(cudaSetDevice(m->p.device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, which == EALS_BUF_U ? m->U : m->V));
+  std::memcpy(handle_out, &h, sizeof(h));
+  return EALS_OK;
+}
+
+int eals_ipc_detach(eals_model* m) {
+  if (!m) return EALS_OK;
+  cudaSetDevice(m->p.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (eals::PeerSet* ps : {&m->peersU, &m->peersV}) {
+    for (int p = 0; p < ps->n; p++) cudaIpcCloseMemHandle(ps->x[p]);
+    ps->n = 0;
+  }
+  return EALS_OK;
+}
+
+int eals_ipc_attach(eals_model* m, int32_t which, int32_t n_peers, const void* handles) {
+  if (!m || (!handles && n_peers > 0)) return fail(EALS_ERR_ARG, "null argument");
+  if (which != EALS_BUF_U && which != EALS_BUF_V) return fail(EALS_ERR_ARG, "only U and V can be shared");
+  if (n_peers < 0 || n_peers > eals::kMaxPeers) return fail(EALS_ERR_UNSUPPORTED, "at most %d peers", eals::kMaxPeers);
+  CU(cudaSetDevice(m->p.device));
+  CU(cudaStreamSynchronize(m->stream));
+  eals::PeerSet& ps = which == EALS_BUF_U ? m->peersU : m->peersV;
+  for (int p = 0; p < ps.n; p++) cudaIpcCloseMemHandle(ps.x[p]);
+  ps.n = 0;
+  for (int p = 0; p < n_peers; p++) {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + (size_t)p * EALS_IPC_HANDLE_BYTES, sizeof(h));
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ps.x[ps.n++] = (double*)ptr;
+  }
   return EALS_OK;
 }
 

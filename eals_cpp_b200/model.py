@@ -21,6 +21,7 @@ the partial K x K Grams are all-reduced.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import sys
 import time
 from dataclasses import dataclass
@@ -194,10 +195,33 @@ class MF_fastALS:
         import torch
         with torch.cuda.device(self.device):
             check(self.lib.eals_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream), 0))
+        self.peer_store = False
+        if self.world > 1 and os.environ.get("EALS_PEER_STORE", "1") != "0":
+            self._attach_peers()
         if init:
             check(self.lib.eals_init_factors(self.h))     # MF_fastALS.cpp:85-90
 
     # ---- helpers ---------------------------------------------------------------------------------
+    def _attach_peers(self):
+        """Exchange the CUDA IPC handles of the U and V replicas and map the other ranks' buffers, so
+        that the sweep kernels store finished rows into every replica themselves (the all-gather of
+        SURVEY.md §8e fused into the sweep).  Needs all ranks on one box with peer access."""
+        import torch
+        import torch.distributed as dist
+        if self.world - 1 > 7:
+            return
+        dev = f"cuda:{self.device}"
+        for which in (_lib.BUF_U, _lib.BUF_V):
+            mine = np.zeros(64, np.uint8)
+            check(self.lib.eals_ipc_handle(self.h, which, _ptr(mine)))
+            t = torch.from_numpy(mine).to(dev)
+            allh = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(allh, t, group=self.group)
+            others = np.concatenate([allh[r].cpu().numpy() for r in range(self.world) if r != self.rank])
+            others = np.ascontiguousarray(others, np.uint8)
+            check(self.lib.eals_ipc_attach(self.h, which, self.world - 1, _ptr(others)))
+        self.peer_store = True
+
     def _test_items(self, testRatings):
         a = np.asarray(testRatings)
         if a.ndim == 2:                                  # rows of (userId, itemId, ...) like Rating.h
@@ -296,7 +320,7 @@ class MF_fastALS:
     def update_user(self):
         """User sweep + SU refresh (MF_fastALS.cpp:127-132)."""
         check(self.lib.eals_sweep_users(self.h))
-        if self.world > 1:
+        if self.world > 1 and not self.peer_store:
             exchange_rows(self.device_tensor(_lib.BUF_U), self.user_bounds, self.rank, self.group)
         check(self.lib.eals_gram_users(self.h))
         if self.world > 1:
@@ -305,7 +329,7 @@ class MF_fastALS:
     def update_item(self):
         """Item sweep + SV refresh (MF_fastALS.cpp:146-152)."""
         check(self.lib.eals_sweep_items(self.h))
-        if self.world > 1:
+        if self.world > 1 and not self.peer_store:
             exchange_rows(self.device_tensor(_lib.BUF_V), self.item_bounds, self.rank, self.group)
         check(self.lib.eals_gram_items(self.h))
         if self.world > 1:

@@ -182,6 +182,17 @@ int eals_stream(eals_model* m, void** cuda_stream);        /* cudaStream_t the m
  * Synchronises the old stream first. */
 int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own);
 int eals_sync(eals_model* m);
+/* Fused exchange of the updated factor rows (one process per GPU, all on one NVLink box).
+ * eals_ipc_handle writes the 64-byte CUDA IPC handle of this model's U or V replica
+ * (which = EALS_BUF_U / EALS_BUF_V); after the host has exchanged the handles, eals_ipc_attach maps
+ * the n_peers (<= 7) OTHER ranks' replicas (handles = n_peers x 64 bytes).  From then on the sweep
+ * kernels store every finished row into all replicas themselves, so no all-gather is needed after a
+ * sweep — only the all-reduce of the partial Gram, which also orders the stores.  eals_ipc_detach
+ * unmaps the peers (also done by eals_destroy). */
+#define EALS_IPC_HANDLE_BYTES 64
+int eals_ipc_handle(eals_model* m, int32_t which, void* handle_out);
+int eals_ipc_attach(eals_model* m, int32_t which, int32_t n_peers, const void* handles);
+int eals_ipc_detach(eals_model* m);
 int64_t eals_nnz(const eals_model* m);                     /* nonzeros of the owned user rows     */
 int64_t eals_kernel_launches(const eals_model* m);         /* kernels launched so far             */
 /* Device milliseconds of the most recent call of each kind: [0] user sweep, [1] user Gram,
