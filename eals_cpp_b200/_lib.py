@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libeals_b200.so")
 
 EALS_HOST, EALS_DEVICE = 0, 1
-BUF_U, BUF_V, BUF_SU, BUF_SV, BUF_WI, BUF_LOSS_TERMS = range(6)
+BUF_U, BUF_V, BUF_SU, BUF_SV, BUF_WI, BUF_LOSS_TERMS, BUF_PC_USER, BUF_PC_ITEM = range(8)
 EVAL_REFERENCE, EVAL_EXACT = 0, 1
 FLAG_SYNC_EACH_CALL = 1
 
@@ -27,6 +27,8 @@ class EalsParams(C.Structure):
         ("user_begin", C.c_int32), ("user_end", C.c_int32),
         ("item_begin", C.c_int32), ("item_end", C.c_int32),
         ("flags", C.c_int32), ("reserved", C.c_int32),
+        ("n_ranks", C.c_int32), ("rank", C.c_int32),
+        ("user_bounds", C.c_int32 * 9), ("item_bounds", C.c_int32 * 9),
     ]
 
 

@@ -193,7 +193,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
         const double w = a.val ? a.val[p0 + j] : 1.0;
         wr[m] = w * w;
         cw[m] = w - (USER ? a.Wi[id] : wi_row);
-        if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
+        if (a.use_cache) pr[m] = a.pc_in[p0 + j];
       }
       c_s[j] = cw[m];
       z_s[j] = 0.0;
@@ -323,11 +323,11 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
       }
     }
     for (int k = lane; k < K; k += 32) store_row_value(a, (size_t)grow * LD + k, x_s[k]);
-    if (a.pcache) {
+    if (a.pc_out.n) {
 #pragma unroll
       for (int m = 0; m < MAXM; m++) {
         const int j = m * 32 + lane;
-        if (j < n) a.pcache[cache_pos(a, p0 + j)] = pr[m];
+        if (j < n) pc_store(a, p0 + j, pr[m]);
       }
     }
     __syncwarp();
@@ -400,7 +400,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       const double w = a.val ? a.val[p0 + j] : 1.0;
       wr[m] = w * w;
       cw[m] = w - (USER ? a.Wi[id] : wi_row);
-      if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
+      if (a.use_cache) pr[m] = a.pc_in[p0 + j];
     }
     c_s[j] = cw[m];
     z_s[j] = 0.0;
@@ -547,11 +547,11 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
     }
   }
   for (int k = tid; k < K; k += kT) store_row_value(a, (size_t)grow * LD + k, x_s[k]);
-  if (a.pcache) {
+  if (a.pc_out.n) {
 #pragma unroll
     for (int m = 0; m < MW; m++) {
       const int j = m * kT + tid;
-      if (j < n) a.pcache[cache_pos(a, p0 + j)] = pr[m];
+      if (j < n) pc_store(a, p0 + j, pr[m]);
     }
   }
 }
@@ -648,7 +648,7 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
     const double w = a.val ? a.val[off + tid] : 1.0;
     wr = w * w;
     cw = w - (USER ? a.Wi[id] : wi_row);
-    pr = (fb == 0 && a.use_cache) ? a.pcache[cache_pos(a, off + tid)] : pred[poff + tid];
+    pr = (fb == 0 && a.use_cache) ? a.pc_in[off + tid] : pred[poff + tid];
   }
   c_s[tid] = cw;
   if (fb > 0 && tid < 16) delta_s[tid] = delta[(size_t)hu.unit_hrow[u] * 16 + tid];
@@ -678,7 +678,7 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
       }
       pr = (a0 + a1) + (a2 + a3);
       if (fb < nblocks) pred[poff + tid] = pr;
-      else if (a.pcache) a.pcache[cache_pos(a, off + tid)] = pr;   // final value -> symmetric cache
+      else if (a.pc_out.n) pc_store(a, off + tid, pr);   // final value -> symmetric cache
     }
   } else if (a.use_cache && tid < n) {
     pred[poff + tid] = pr;   // the pipeline's compact cache starts from the symmetric one

@@ -35,6 +35,13 @@ struct PeerSet {
   int n;
 };
 
+// The other orientation's prediction caches: rank r holds global positions [bound[r], bound[r+1]).
+struct PcOut {
+  double* base[8];
+  uint32_t bound[9];
+  int n;                   // ranks (0: no cache)
+};
+
 struct CdSide {
   const int64_t* ptr;   // [rows+1] offsets of the owned rows (first owned row at 0)
   const int32_t* idx;   // neighbour ids, ascending inside a row
@@ -46,13 +53,15 @@ struct CdSide {
   int row_base;         // global id of owned row 0
   int K;
   double reg;
-  // Symmetric prediction cache (single-rank models): pcache[q] = <u, v> of nonzero q in CSR order.
-  // The value a user sweep leaves behind is exactly the one the item sweep starts from (and vice
-  // versa), so the gather pass that rebuilds it (MF_fastALS.cpp:261-270 / 352-363) is skipped.
-  // perm maps this side's nonzero positions to CSR positions (nullptr on the user side).
-  double* pcache;       // nullptr: no cache
-  const uint32_t* perm;
-  int use_cache;        // 1: pcache is valid on entry, read it instead of recomputing
+  // Symmetric prediction cache.  The prediction <u, v> a user sweep leaves behind for a nonzero is
+  // exactly the value the item sweep starts from (and vice versa), so the gather pass that rebuilds
+  // it (MF_fastALS.cpp:261-270 / 352-363) is skipped: each side READS its own cache sequentially
+  // (pc_in, this side's nonzero order) and WRITES the other side's cache at the position of the
+  // same nonzero in the other orientation (pc_map), on whichever rank owns that row (pc_out).
+  const double* pc_in;     // nullptr: no cache
+  const uint32_t* pc_map;  // per local nonzero: its global position in the other orientation
+  PcOut pc_out;
+  int use_cache;           // 1: pc_in is valid on entry, read it instead of recomputing
   PeerSet peers;        // other ranks' replicas of X (n = 0: none)
 };
 
@@ -61,7 +70,13 @@ __device__ __forceinline__ void store_row_value(const CdSide& a, size_t off, dou
   for (int p = 0; p < a.peers.n; p++) a.peers.x[p][off] = v;
 }
 
-__device__ __forceinline__ int64_t cache_pos(const CdSide& a, int64_t q) { return a.perm ? (int64_t)a.perm[q] : q; }
+__device__ __forceinline__ void pc_store(const CdSide& a, int64_t local_pos, double v) {
+  const uint32_t g = a.pc_map[local_pos];
+  int r = 0;
+#pragma unroll
+  for (int t = 1; t < 8; t++) r += (t < a.pc_out.n && g >= a.pc_out.bound[t]) ? 1 : 0;
+  a.pc_out.base[r][g - a.pc_out.bound[r]] = v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Warp-per-row kernel: rows with 1..32*MAXM nonzeros.  Lane l owns nonzeros l, l+32, ...; their
@@ -135,7 +150,7 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
       const double w = a.val ? a.val[p0 + j] : 1.0;
       wr[m] = w * w;                                   // w_ui * r_ui, both are the stored value
       cw[m] = w - (USER ? a.Wi[id] : wi_row);
-      if (a.use_cache) pr[m] = a.pcache[cache_pos(a, p0 + j)];
+      if (a.use_cache) pr[m] = a.pc_in[p0 + j];
     }
   }
   __syncwarp();
@@ -193,10 +208,10 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
     }
   }
   for (int k = lane; k < K; k += 32) store_row_value(a, (size_t)grow * LD + k, u_s[k]);
-  if (a.pcache) {
+  if (a.pc_out.n) {
 #pragma unroll
     for (int m = 0; m < MAXM; m++)
-      if (ok[m]) a.pcache[cache_pos(a, p0 + m * 32 + lane)] = pr[m];
+      if (ok[m]) pc_store(a, p0 + m * 32 + lane, pr[m]);
   }
 }
 

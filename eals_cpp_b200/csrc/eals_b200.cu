@@ -159,11 +159,17 @@ struct eals_model {
   bool factors_set = false;
   eals::PeerSet peersU = {}, peersV = {};   // IPC mappings of the other ranks' U / V replicas
   // symmetric prediction cache (single-rank models only)
-  double* pcache = nullptr;      // [nnz] in CSR order
-  uint32_t* csc2csr = nullptr;   // CSC position -> CSR position
-  size_t cap_pcache = 0, cap_csc2csr = 0;
+  double* pc_u = nullptr;        // predictions of the owned user rows' nonzeros (CSR order)
+  double* pc_i = nullptr;        // predictions of the owned item columns' nonzeros (CSC order)
+  uint32_t* map_u = nullptr;     // owned CSR nonzero -> global CSC position of the same nonzero
+  uint32_t* map_i = nullptr;     // owned CSC nonzero -> global CSR position
+  size_t cap_pc_u = 0, cap_pc_i = 0, cap_map_u = 0, cap_map_i = 0;
+  eals::PcOut out_to_items = {}, out_to_users = {};   // where the other side's caches live (all ranks)
+  int n_ranks = 1, rank = 0;
+  bool pc_attached = false;      // caches usable: single rank, or both peers' cache sets mapped
+  bool pc_users_attached = false, pc_items_attached = false;
   bool pcache_on = false;        // structures built for the current matrix
-  bool pcache_valid = false;
+  bool pc_u_valid = false, pc_i_valid = false;
   int sweeps_since_fresh = 0;
   int pred_refresh_every = 0;    // EALS_PRED_REFRESH_EVERY: recompute the cache from scratch every n sweeps (0 = never)
 };
@@ -221,24 +227,25 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ ptr, const int32
 
 int ensure_partials(eals_model* m, size_t n);
 
-// csc2csr[q] = position in the CSR arrays of the nonzero stored at CSC position q.
-__global__ void build_csc2csr_kernel(const int64_t* __restrict__ col_ptr, const int32_t* __restrict__ row_idx, int N,
-                                     const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-                                     int64_t nnz, uint32_t* __restrict__ perm) {
+// For every nonzero of the local slice of orientation A (rows [a0, a0 + rowsA), offsets rebased to
+// 0): the GLOBAL position of the same nonzero in orientation B (full offsets/indices).
+__global__ void build_map_kernel(const int64_t* __restrict__ ptrA, const int32_t* __restrict__ idxA, int rowsA, int a0,
+                                 const int64_t* __restrict__ ptrB_full, const int32_t* __restrict__ idxB_full,
+                                 int64_t nnzA, uint32_t* __restrict__ map) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nnz) return;
-  int lo = 0, hi = N;                       // largest i with col_ptr[i] <= q
+  if (q >= nnzA) return;
+  int lo = 0, hi = rowsA;                   // largest local row with ptrA[row] <= q
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if (col_ptr[mid] <= q) lo = mid; else hi = mid;
+    if (ptrA[mid] <= q) lo = mid; else hi = mid;
   }
-  const int i = lo, u = row_idx[q];
-  int64_t a = row_ptr[u], b = row_ptr[u + 1];
+  const int r = a0 + lo, c = idxA[q];
+  int64_t a = ptrB_full[c], b = ptrB_full[c + 1];
   while (b - a > 1) {
     const int64_t mid = (a + b) >> 1;
-    if (col_idx[mid] <= i) a = mid; else b = mid;
+    if (idxB_full[mid] <= r) a = mid; else b = mid;
   }
-  perm[q] = col_idx[a] == i ? (uint32_t)a : 0xffffffffu;
+  map[q] = (b > a && idxB_full[a] == r) ? (uint32_t)a : 0xffffffffu;
 }
 
 __global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz, int* __restrict__ bad) {
@@ -246,31 +253,96 @@ __global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz
   if (q < nnz && perm[q] == 0xffffffffu) atomicExch(bad, 1);
 }
 
-// (Re)build the symmetric prediction cache structures after the matrix changed.
-int build_pred_cache(eals_model* m) {
+// Unmap the other ranks' prediction caches (multi-rank models).
+void close_pc_peers(eals_model* m, eals::PcOut& out, bool& attached_flag) {
+  for (int r = 0; r < out.n; r++)
+    if (r != m->rank && out.base[r]) { cudaIpcCloseMemHandle(out.base[r]); out.base[r] = nullptr; }
+  attached_flag = false;
+}
+
+// (Re)build the symmetric prediction cache structures after the matrix changed.  Needs the FULL
+// offsets and index arrays of both orientations (the arguments of eals_create / eals_set_train).
+int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int32_t* col_idx,
+                     const int64_t* col_ptr, const int32_t* row_idx) {
   StageTimer tm;
-  m->pcache_valid = false;
+  m->pc_u_valid = m->pc_i_valid = false;
   m->pcache_on = false;
-  const bool single_rank = m->ub == 0 && m->ue == m->M && m->ib == 0 && m->ie == m->N;
-  const int64_t nnz = m->users.nnz;
+  if (m->n_ranks > 1) {   // the peers' mappings belong to the previous matrix
+    CU(cudaStreamSynchronize(m->stream));
+    close_pc_peers(m, m->out_to_users, m->pc_users_attached);
+    close_pc_peers(m, m->out_to_items, m->pc_items_attached);
+  }
+  m->pc_attached = false;
+  const bool single = m->ub == 0 && m->ue == m->M && m->ib == 0 && m->ie == m->N;
+  const bool multi = !single && m->n_ranks > 1;
   const char* off = getenv("EALS_NO_PRED_CACHE");
-  if (!single_rank || nnz == 0 || nnz >= 0xffffffffLL || nnz != m->items.nnz || (off && off[0] == '1')) return EALS_OK;
-  OK(dev_reserve(&m->pcache, &m->cap_pcache, (size_t)nnz));
-  OK(dev_reserve(&m->csc2csr, &m->cap_csc2csr, (size_t)nnz));
-  const unsigned grid = (unsigned)((nnz + 255) / 256);
-  build_csc2csr_kernel<<<grid, 256, 0, m->stream>>>(m->items.ptr, m->items.idx, m->N, m->users.ptr, m->users.idx, nnz, m->csc2csr);
+  if ((!single && !multi) || m->users.nnz == 0 || m->items.nnz == 0 || (off && off[0] == '1')) return EALS_OK;
+  // total nonzeros must fit the 32-bit positions of the maps
+  std::vector<int64_t> rp((size_t)m->n_ranks + 1), cp((size_t)m->n_ranks + 1);
+  auto fetch = [&](const int64_t* src, int64_t at, int64_t* dst) -> int {
+    if (space == EALS_DEVICE) CU(cudaMemcpy(dst, src + at, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    else *dst = src[at];
+    return EALS_OK;
+  };
+  int64_t nnz_total = 0;
+  OK(fetch(row_ptr, m->M, &nnz_total));
+  if (nnz_total >= 0xffffffffLL) return EALS_OK;
+  for (int r = 0; r <= m->n_ranks; r++) {
+    OK(fetch(row_ptr, single ? (r ? m->M : 0) : m->p.user_bounds[r], &rp[r]));
+    OK(fetch(col_ptr, single ? (r ? m->N : 0) : m->p.item_bounds[r], &cp[r]));
+  }
+  // full arrays of the OTHER orientation on the device (temporary copies when the input is on the host
+  // and this model holds only a slice)
+  const int64_t* d_rp = nullptr; const int32_t* d_ci = nullptr; const int64_t* d_cp = nullptr; const int32_t* d_ri = nullptr;
+  int64_t *t_rp = nullptr, *t_cp = nullptr; int32_t *t_ci = nullptr, *t_ri = nullptr;
+  if (single) {
+    d_rp = m->users.ptr; d_ci = m->users.idx; d_cp = m->items.ptr; d_ri = m->items.idx;
+  } else if (space == EALS_DEVICE) {
+    d_rp = row_ptr; d_ci = col_idx; d_cp = col_ptr; d_ri = row_idx;
+  } else {
+    OK(dev_alloc(&t_rp, (size_t)m->M + 1)); OK(dev_alloc(&t_cp, (size_t)m->N + 1));
+    OK(dev_alloc(&t_ci, (size_t)nnz_total)); OK(dev_alloc(&t_ri, (size_t)nnz_total));
+    CU(cudaMemcpyAsync(t_rp, row_ptr, sizeof(int64_t) * (m->M + 1), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(t_cp, col_ptr, sizeof(int64_t) * (m->N + 1), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(t_ci, col_idx, sizeof(int32_t) * nnz_total, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(t_ri, row_idx, sizeof(int32_t) * nnz_total, cudaMemcpyHostToDevice, m->stream));
+    d_rp = t_rp; d_ci = t_ci; d_cp = t_cp; d_ri = t_ri;
+  }
+  const int64_t nu = m->users.nnz, ni = m->items.nnz;
+  OK(dev_reserve(&m->pc_u, &m->cap_pc_u, (size_t)nu));
+  OK(dev_reserve(&m->pc_i, &m->cap_pc_i, (size_t)ni));
+  OK(dev_reserve(&m->map_u, &m->cap_map_u, (size_t)nu));
+  OK(dev_reserve(&m->map_i, &m->cap_map_i, (size_t)ni));
+  build_map_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, m->stream>>>(m->users.ptr, m->users.idx, m->users.rows, m->ub,
+                                                                       d_cp, d_ri, nu, m->map_u);
+  OK(check_launch(m));
+  build_map_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, m->stream>>>(m->items.ptr, m->items.idx, m->items.rows, m->ib,
+                                                                       d_rp, d_ci, ni, m->map_i);
   OK(check_launch(m));
   int* bad;
   OK(dev_alloc(&bad, 1));
   CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
-  check_perm_kernel<<<grid, 256, 0, m->stream>>>(m->csc2csr, nnz, bad);
+  check_perm_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, m->stream>>>(m->map_u, nu, bad);
+  OK(check_launch(m));
+  check_perm_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, m->stream>>>(m->map_i, ni, bad);
   OK(check_launch(m));
   int h_bad = 0;
   CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
-  cudaFree(bad);
+  cudaFree(bad); cudaFree(t_rp); cudaFree(t_cp); cudaFree(t_ci); cudaFree(t_ri);
   if (h_bad) return fail(EALS_ERR_ARG, "the CSR and CSC arrays do not describe the same matrix");
-  tm.lap("pred cache: csc->csr map");
+  // destination tables; the own rank's entries are filled now, the peers' by eals_ipc_attach
+  const int nr = single ? 1 : m->n_ranks, me = single ? 0 : m->rank;
+  m->out_to_items = eals::PcOut{}; m->out_to_users = eals::PcOut{};
+  m->out_to_items.n = m->out_to_users.n = nr;
+  for (int r = 0; r <= nr; r++) {
+    m->out_to_items.bound[r] = (uint32_t)cp[r];   // user sweeps write CSC-ordered caches
+    m->out_to_users.bound[r] = (uint32_t)rp[r];   // item sweeps write CSR-ordered caches
+  }
+  m->out_to_items.base[me] = m->pc_i;
+  m->out_to_users.base[me] = m->pc_u;
+  m->pc_attached = single;
+  tm.lap("pred cache: position maps");
   m->pcache_on = true;
   if (const char* e = getenv("EALS_PRED_REFRESH_EVERY")) m->pred_refresh_every = atoi(e);
   return EALS_OK;
@@ -586,7 +658,7 @@ int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b
   }
   for (int fb = 0; fb <= nblocks; fb++) {
     if (fb == nblocks) {   // last cache update; only needed when the symmetric cache keeps the result
-      if (!a.pcache) break;
+      if (!a.pc_out.n) break;
       step<<<nu, eals::kBlkThreads, eals::HeavySmem::kBytes, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
       OK(check_launch(m));
       break;
@@ -665,17 +737,21 @@ int sweep(eals_model* m, bool user, int only_row) {
   a.row_base = s.row_base;
   a.K = m->K;
   a.reg = m->p.reg;
-  a.pcache = nullptr; a.perm = nullptr; a.use_cache = 0;
+  a.pc_in = nullptr; a.pc_map = nullptr; a.pc_out = eals::PcOut{}; a.use_cache = 0;
   a.peers = user ? m->peersU : m->peersV;
   if (only_row >= 0) {
-    m->pcache_valid = false;           // a single-row update changes factors behind the cache's back
-  } else if (m->pcache_on) {
-    if (m->pred_refresh_every > 0 && m->sweeps_since_fresh >= m->pred_refresh_every) m->pcache_valid = false;
-    a.pcache = m->pcache;
-    a.perm = user ? nullptr : m->csc2csr;
-    a.use_cache = m->pcache_valid ? 1 : 0;
-    m->sweeps_since_fresh = m->pcache_valid ? m->sweeps_since_fresh + 1 : 0;
-    m->pcache_valid = true;            // every nonzero's final prediction is stored by this sweep
+    m->pc_u_valid = m->pc_i_valid = false;   // a single-row update changes factors behind the cache's back
+  } else if (m->pcache_on && m->pc_attached) {
+    bool& in_valid = user ? m->pc_u_valid : m->pc_i_valid;
+    bool& out_valid = user ? m->pc_i_valid : m->pc_u_valid;
+    if (m->pred_refresh_every > 0 && m->sweeps_since_fresh >= m->pred_refresh_every) in_valid = false;
+    a.pc_in = user ? m->pc_u : m->pc_i;
+    a.pc_map = user ? m->map_u : m->map_i;
+    a.pc_out = user ? m->out_to_items : m->out_to_users;
+    a.use_cache = in_valid ? 1 : 0;
+    m->sweeps_since_fresh = in_valid ? m->sweeps_since_fresh + 1 : 0;
+    in_valid = false;    // this side's cache describes the factors BEFORE this sweep
+    out_valid = true;    // every nonzero's final prediction is stored on the other side by this sweep
   }
   if (user) { DISPATCH_LD(m->LD, OK((launch_cd<LD, true>(m, s, a, only_row)))); }
   else      { DISPATCH_LD(m->LD, OK((launch_cd<LD, false>(m, s, a, only_row)))); }
@@ -790,10 +866,10 @@ int loss_terms(eals_model* m, double terms[4]) {
   a.ptr = s.ptr; a.idx = s.idx; a.val = s.val;
   a.X = m->U; a.Y = m->V; a.Wi = m->Wi; a.row_base = s.row_base;
   int np = 0;
-  if (m->pcache_on && m->pcache_valid) {   // every prediction is already cached: stream it, no gather
+  if (m->pcache_on && m->pc_attached && m->pc_u_valid) {   // every prediction is already cached: stream it, no gather
     np = 8 * m->sm_count;
     OK(ensure_partials(m, (size_t)np));
-    eals::loss_cached_kernel<<<np, eals::kLossThreads, 0, m->stream>>>(s.idx, s.val, m->pcache, m->Wi, s.nnz, m->partials);
+    eals::loss_cached_kernel<<<np, eals::kLossThreads, 0, m->stream>>>(s.idx, s.val, m->pc_u, m->Wi, s.nnz, m->partials);
     OK(check_launch(m));
   } else {
     DISPATCH_LD(m->LD, OK(launch_loss_rows<LD>(m, a, s, &np)));
@@ -1029,7 +1105,8 @@ int eals_destroy(eals_model* m) {
   free_side(m->users);
   free_side(m->items);
   cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
-  cudaFree(m->terms); cudaFree(m->partials); cudaFree(m->pcache); cudaFree(m->csc2csr);
+  cudaFree(m->terms); cudaFree(m->partials);
+  cudaFree(m->pc_u); cudaFree(m->pc_i); cudaFree(m->map_u); cudaFree(m->map_i);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -1065,9 +1142,21 @@ int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t
   m->ib = params->item_begin; m->ie = params->item_end;
   if (m->ub == 0 && m->ue == 0) m->ue = m->M;
   if (m->ib == 0 && m->ie == 0) m->ie = m->N;
+  m->n_ranks = std::max(1, params->n_ranks);
+  m->rank = params->rank;
   auto bail = [&](int code) { eals_destroy(m); return code; };
   if (m->ub < 0 || m->ue > m->M || m->ub > m->ue || m->ib < 0 || m->ie > m->N || m->ib > m->ie)
     return bail(fail(EALS_ERR_ARG, "owned ranges out of bounds"));
+  if (m->n_ranks > 1) {
+    const eals_params& q = *params;
+    bool ok = m->n_ranks <= 8 && q.rank >= 0 && q.rank < m->n_ranks && q.user_bounds[0] == 0 && q.item_bounds[0] == 0 &&
+              q.user_bounds[m->n_ranks] == m->M && q.item_bounds[m->n_ranks] == m->N &&
+              q.user_bounds[q.rank] == m->ub && q.user_bounds[q.rank + 1] == m->ue &&
+              q.item_bounds[q.rank] == m->ib && q.item_bounds[q.rank + 1] == m->ie;
+    for (int r = 0; ok && r < m->n_ranks; r++)
+      ok = q.user_bounds[r] <= q.user_bounds[r + 1] && q.item_bounds[r] <= q.item_bounds[r + 1];
+    if (!ok) return bail(fail(EALS_ERR_ARG, "inconsistent multi-rank layout (n_ranks, rank, user_bounds, item_bounds)"));
+  }
 
 #define TRY(call) do { int r__ = (call); if (r__ != EALS_OK) return bail(r__); } while (0)
 #define TRYCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(EALS_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e__))); } while (0)
@@ -1089,7 +1178,7 @@ int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t
   TRY(build_side(m, m->users, m->ub, m->ue, m->N, params->input_space, row_ptr, col_idx, row_val));
   TRY(build_side(m, m->items, m->ib, m->ie, m->M, params->input_space, col_ptr, row_idx, col_val));
   TRY(compute_item_weights(m, params->input_space, col_ptr));
-  TRY(build_pred_cache(m));
+  TRY(build_pred_cache(m, params->input_space, row_ptr, col_idx, col_ptr, row_idx));
   TRYCU(cudaStreamSynchronize(m->stream));
 #undef TRY
 #undef TRYCU
@@ -1105,7 +1194,7 @@ int eals_set_train(eals_model* m, int32_t input_space, const int64_t* row_ptr, c
   CU(cudaSetDevice(m->p.device));
   OK(build_side(m, m->users, m->ub, m->ue, m->N, input_space, row_ptr, col_idx, row_val));
   OK(build_side(m, m->items, m->ib, m->ie, m->M, input_space, col_ptr, row_idx, col_val));
-  return build_pred_cache(m);
+  return build_pred_cache(m, input_space, row_ptr, col_idx, col_ptr, row_idx);
 }
 
 int eals_refresh_S(eals_model* m) {
@@ -1135,7 +1224,7 @@ int eals_init_factors(eals_model* m) {
   OK(upload_dense(m, m->V, stream.data(), (size_t)m->N, EALS_HOST));
   CU(cudaStreamSynchronize(m->stream));
   m->factors_set = true;
-  m->pcache_valid = false;
+  m->pc_u_valid = m->pc_i_valid = false;
   return eals_refresh_S(m);
 }
 
@@ -1146,7 +1235,7 @@ int eals_set_factors(eals_model* m, int32_t space, const double* U, const double
   if (V) OK(upload_dense(m, m->V, V, (size_t)m->N, space));
   CU(cudaStreamSynchronize(m->stream));
   m->factors_set = true;
-  m->pcache_valid = false;
+  m->pc_u_valid = m->pc_i_valid = false;
   return eals_refresh_S(m);
 }
 
@@ -1324,12 +1413,14 @@ int eals_device_buffer(eals_model* m, int32_t which, void** dev_ptr, int64_t* by
   int64_t b = 0;
   switch (which) {
     // handing out U or V lets the caller change factors behind the prediction cache's back
-    case EALS_BUF_U: p = m->U; b = (int64_t)m->M * m->LD * 8; m->pcache_valid = false; break;
-    case EALS_BUF_V: p = m->V; b = (int64_t)m->N * m->LD * 8; m->pcache_valid = false; break;
+    case EALS_BUF_U: p = m->U; b = (int64_t)m->M * m->LD * 8; m->pc_u_valid = m->pc_i_valid = false; break;
+    case EALS_BUF_V: p = m->V; b = (int64_t)m->N * m->LD * 8; m->pc_u_valid = m->pc_i_valid = false; break;
     case EALS_BUF_SU: p = m->SU; b = (int64_t)m->K * m->LD * 8; break;
     case EALS_BUF_SV: p = m->SV; b = (int64_t)m->K * m->LD * 8; break;
     case EALS_BUF_WI: p = m->Wi; b = (int64_t)m->N * 8; break;
     case EALS_BUF_LOSS_TERMS: p = m->terms; b = 32; break;
+    case EALS_BUF_PC_USER: p = m->pc_u; b = m->pcache_on ? m->users.nnz * 8 : 0; break;
+    case EALS_BUF_PC_ITEM: p = m->pc_i; b = m->pcache_on ? m->items.nnz * 8 : 0; break;
     default: return fail(EALS_ERR_ARG, "unknown buffer %d", which);
   }
   *dev_ptr = p;
@@ -1354,11 +1445,19 @@ int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own) {
 
 int eals_ipc_handle(eals_model* m, int32_t which, void* handle_out) {
   if (!m || !handle_out) return fail(EALS_ERR_ARG, "null argument");
-  if (which != EALS_BUF_U && which != EALS_BUF_V) return fail(EALS_ERR_ARG, "only U and V can be shared");
   static_assert(sizeof(cudaIpcMemHandle_t) == EALS_IPC_HANDLE_BYTES, "IPC handle size");
+  void* buf = nullptr;
+  switch (which) {
+    case EALS_BUF_U: buf = m->U; break;
+    case EALS_BUF_V: buf = m->V; break;
+    case EALS_BUF_PC_USER: buf = m->pc_u; break;
+    case EALS_BUF_PC_ITEM: buf = m->pc_i; break;
+    default: return fail(EALS_ERR_ARG, "only U, V and the prediction caches can be shared");
+  }
+  if (!buf) return fail(EALS_ERR_STATE, "buffer %d does not exist on this model (prediction cache off?)", which);
   CU(cudaSetDevice(m->p.device));
   cudaIpcMemHandle_t h;
-  CU(cudaIpcGetMemHandle(&h, which == EALS_BUF_U ? m->U : m->V));
+  CU(cudaIpcGetMemHandle(&h, buf));
   std::memcpy(handle_out, &h, sizeof(h));
   return EALS_OK;
 }
@@ -1371,15 +1470,42 @@ int eals_ipc_detach(eals_model* m) {
     for (int p = 0; p < ps->n; p++) cudaIpcCloseMemHandle(ps->x[p]);
     ps->n = 0;
   }
+  if (m->n_ranks > 1) {
+    close_pc_peers(m, m->out_to_users, m->pc_users_attached);
+    close_pc_peers(m, m->out_to_items, m->pc_items_attached);
+    m->pc_attached = false;
+    m->pc_u_valid = m->pc_i_valid = false;
+  }
   return EALS_OK;
 }
 
 int eals_ipc_attach(eals_model* m, int32_t which, int32_t n_peers, const void* handles) {
   if (!m || (!handles && n_peers > 0)) return fail(EALS_ERR_ARG, "null argument");
-  if (which != EALS_BUF_U && which != EALS_BUF_V) return fail(EALS_ERR_ARG, "only U and V can be shared");
   if (n_peers < 0 || n_peers > eals::kMaxPeers) return fail(EALS_ERR_UNSUPPORTED, "at most %d peers", eals::kMaxPeers);
   CU(cudaSetDevice(m->p.device));
   CU(cudaStreamSynchronize(m->stream));
+  if (which == EALS_BUF_PC_USER || which == EALS_BUF_PC_ITEM) {
+    if (!m->pcache_on) return fail(EALS_ERR_STATE, "prediction cache is off on this model");
+    if (m->n_ranks < 2 || n_peers != m->n_ranks - 1)
+      return fail(EALS_ERR_ARG, "prediction caches need eals_params.n_ranks - 1 = %d peer handles, got %d", m->n_ranks - 1, n_peers);
+    eals::PcOut& out = which == EALS_BUF_PC_USER ? m->out_to_users : m->out_to_items;
+    bool& flag = which == EALS_BUF_PC_USER ? m->pc_users_attached : m->pc_items_attached;
+    close_pc_peers(m, out, flag);
+    int p = 0;
+    for (int r = 0; r < m->n_ranks; r++) {
+      if (r == m->rank) continue;
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const char*)handles + (size_t)p++ * EALS_IPC_HANDLE_BYTES, sizeof(h));
+      void* ptr = nullptr;
+      CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      out.base[r] = (double*)ptr;
+    }
+    flag = true;
+    m->pc_attached = m->pc_users_attached && m->pc_items_attached;
+    m->pc_u_valid = m->pc_i_valid = false;
+    return EALS_OK;
+  }
+  if (which != EALS_BUF_U && which != EALS_BUF_V) return fail(EALS_ERR_ARG, "only U, V and the prediction caches can be shared");
   eals::PeerSet& ps = which == EALS_BUF_U ? m->peersU : m->peersV;
   for (int p = 0; p < ps.n; p++) cudaIpcCloseMemHandle(ps.x[p]);
   ps.n = 0;

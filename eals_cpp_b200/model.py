@@ -183,6 +183,10 @@ class MF_fastALS:
         p.user_begin, p.user_end = self.user_bounds[self.rank], self.user_bounds[self.rank + 1]
         p.item_begin, p.item_end = self.item_bounds[self.rank], self.item_bounds[self.rank + 1]
         p.flags = _lib.FLAG_SYNC_EACH_CALL if debug_sync else 0
+        if 1 < self.world <= 8:                           # lets the prediction caches span the ranks
+            p.n_ranks, p.rank = self.world, self.rank
+            for r in range(self.world + 1):
+                p.user_bounds[r], p.item_bounds[r] = self.user_bounds[r], self.item_bounds[r]
         if self.world > 1 and (p.user_end == p.user_begin or p.item_end == p.item_begin):
             raise ValueError("more ranks than rows: a rank would own an empty range")
         self._params = p
@@ -195,7 +199,7 @@ class MF_fastALS:
         import torch
         with torch.cuda.device(self.device):
             check(self.lib.eals_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream), 0))
-        self.peer_store = False
+        self.peer_store = self.peer_pred_cache = False
         if self.world > 1 and os.environ.get("EALS_PEER_STORE", "1") != "0":
             self._attach_peers()
         if init:
@@ -211,7 +215,11 @@ class MF_fastALS:
         if self.world - 1 > 7:
             return
         dev = f"cuda:{self.device}"
-        for which in (_lib.BUF_U, _lib.BUF_V):
+        shared = [_lib.BUF_U, _lib.BUF_V]
+        if os.environ.get("EALS_PEER_PRED_CACHE", "1") != "0" and self._pred_cache_everywhere():
+            shared += [_lib.BUF_PC_USER, _lib.BUF_PC_ITEM]
+        self.peer_pred_cache = len(shared) == 4
+        for which in shared:
             mine = np.zeros(64, np.uint8)
             check(self.lib.eals_ipc_handle(self.h, which, _ptr(mine)))
             t = torch.from_numpy(mine).to(dev)
@@ -221,6 +229,16 @@ class MF_fastALS:
             others = np.ascontiguousarray(others, np.uint8)
             check(self.lib.eals_ipc_attach(self.h, which, self.world - 1, _ptr(others)))
         self.peer_store = True
+
+    def _pred_cache_everywhere(self) -> bool:
+        """True when every rank built its prediction caches (they are skipped e.g. for >= 2^32 nonzeros)."""
+        import torch
+        import torch.distributed as dist
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        check(self.lib.eals_device_buffer(self.h, _lib.BUF_PC_USER, C.byref(ptr), C.byref(nbytes)))
+        ok = torch.tensor([1 if (ptr.value and nbytes.value > 0) else 0], device=f"cuda:{self.device}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(ok.item())
 
     def _test_items(self, testRatings):
         a = np.asarray(testRatings)
@@ -315,6 +333,8 @@ class MF_fastALS:
         check(self.lib.eals_set_train(self.h, space, _ptr(sm.row_ptr), _ptr(sm.col_idx), _ptr(sm.row_val),
                                       _ptr(sm.col_ptr), _ptr(sm.row_idx), _ptr(sm.col_val)))
         self.trainMatrix = sm
+        if self.peer_store:                               # the prediction caches were rebuilt: share them again
+            self._attach_peers()
 
     # ---- half-epochs ---------------------------------------------------------------------------------
     def update_user(self):

@@ -54,7 +54,9 @@ typedef enum eals_buffer {
   EALS_BUF_SU = 2,    /* [factors][ld]  S cache U^T U (this rank's partial until reduced)         */
   EALS_BUF_SV = 3,    /* [factors][ld]  S cache V^T diag(Wi) V                                    */
   EALS_BUF_WI = 4,    /* [n_items]                                                                */
-  EALS_BUF_LOSS_TERMS = 5 /* [4] fp64, see eals_loss_terms                                        */
+  EALS_BUF_LOSS_TERMS = 5,/* [4] fp64, see eals_loss_terms                                        */
+  EALS_BUF_PC_USER = 6,   /* prediction cache of the owned user rows' nonzeros (CSR order)         */
+  EALS_BUF_PC_ITEM = 7    /* prediction cache of the owned item columns' nonzeros (CSC order)      */
 } eals_buffer;
 
 typedef enum eals_eval_mode {
@@ -85,6 +87,14 @@ typedef struct eals_params {
   int32_t item_end;
   int32_t flags;          /* EALS_FLAG_*                                                          */
   int32_t reserved;
+  /* Multi-rank layout (optional; n_ranks <= 1 means this model is alone).  rank r owns users
+   * [user_bounds[r], user_bounds[r+1]) and items [item_bounds[r], item_bounds[r+1]); the entries for
+   * `rank` must equal user_begin/user_end and item_begin/item_end.  With it the symmetric
+   * prediction cache also works across ranks (see eals_ipc_attach). */
+  int32_t n_ranks;        /* 0..8                                                                 */
+  int32_t rank;
+  int32_t user_bounds[9];
+  int32_t item_bounds[9];
 } eals_params;
 
 #define EALS_FLAG_SYNC_EACH_CALL 1 /* debugging: synchronise + check after every enqueue          */
@@ -185,10 +195,14 @@ int eals_sync(eals_model* m);
 /* Fused exchange of the updated factor rows (one process per GPU, all on one NVLink box).
  * eals_ipc_handle writes the 64-byte CUDA IPC handle of this model's U or V replica
  * (which = EALS_BUF_U / EALS_BUF_V); after the host has exchanged the handles, eals_ipc_attach maps
- * the n_peers (<= 7) OTHER ranks' replicas (handles = n_peers x 64 bytes).  From then on the sweep
- * kernels store every finished row into all replicas themselves, so no all-gather is needed after a
- * sweep — only the all-reduce of the partial Gram, which also orders the stores.  eals_ipc_detach
- * unmaps the peers (also done by eals_destroy). */
+ * the n_peers (<= 7) OTHER ranks' replicas (handles = n_peers x 64 bytes, in rank order with the own
+ * rank left out).  From then on the sweep kernels store every finished row into all replicas
+ * themselves, so no all-gather is needed after a sweep — only the all-reduce of the partial Gram,
+ * which also orders the stores.  The same two calls with which = EALS_BUF_PC_USER / EALS_BUF_PC_ITEM
+ * share the prediction caches (needs eals_params.n_ranks > 1): a sweep then leaves the prediction of
+ * each nonzero with the rank that will start from it in the next half-epoch, and no rank has to
+ * re-gather factor rows to rebuild it.  Handles must be exchanged again after eals_set_train.
+ * eals_ipc_detach unmaps all peers (also done by eals_destroy). */
 #define EALS_IPC_HANDLE_BYTES 64
 int eals_ipc_handle(eals_model* m, int32_t which, void* handle_out);
 int eals_ipc_attach(eals_model* m, int32_t which, int32_t n_peers, const void* handles);

@@ -48,7 +48,7 @@ def main():
     assert np.allclose(res, want, rtol=0, atol=1e-12), (res, want)
     dist.barrier()
     if rank == 0:
-        print(f"dist parity ok: world {fals.world}, peer_store {fals.peer_store}, loss {lg!r}")
+        print(f"dist parity ok: world {fals.world}, peer_store {fals.peer_store}, peer_pred_cache {fals.peer_pred_cache}, loss {lg!r}")
     dist.destroy_process_group()
 
 
