@@ -106,14 +106,24 @@ __device__ __forceinline__ void load_tile_row(const unsigned char* tile, int r, 
 //   * the 16-step in-block Gauss-Seidel is multiply/shuffle/fma only (one reciprocal per factor,
 //     taken in parallel before the loop).
 // ---------------------------------------------------------------------------------------------
+// S in shared memory: symmetric, so only the 16 x 16 blocks on and below the block diagonal are
+// kept (LD = 128: 36 blocks, 78 KB instead of 128 KB — the difference buys 50 % more resident
+// row-warps per SM).  Block (bi, bj), bi >= bj, holds S[16 bi + r][16 bj + c] at [r * 17 + c]; the odd
+// row stride makes both the row walk (element of the block's transpose) and the column walk
+// conflict-free across the 16 factor lanes.
+constexpr int kSBlk = 16 * 17;
+__host__ __device__ constexpr int s_tri(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
+
 template <int LD, int MAXM>
 struct WarpBlockSmem {
   static constexpr bool kSInSmem = LD <= 128;
+  static constexpr int kNB = LD / 16;
   static constexpr int kRows = 32 * MAXM;
-  static constexpr size_t kS = kSInSmem ? (size_t)LD * LD * 8 : 0;
+  static constexpr size_t kS = kSInSmem ? (size_t)s_tri(kNB, 0) * kSBlk * 8 : 0;
   static constexpr size_t kTile = (size_t)kRows * 128;
-  // tile | idx | c | z | x | Gs[256] | Pt[16] | delta[16]
+  // tile | row pointers | c | z | x | Gs[256] | Pt[16] | delta[16]
   static constexpr size_t kBytesPerWarp = kTile + (size_t)kRows * (8 + 8 + 8) + (size_t)LD * 8 + (256 + 16 + 16) * 8;
+  static constexpr int kMaxWarps = MAXM == 1 ? 16 : (MAXM == 2 ? 11 : 6);
 };
 
 // Gram + right-hand-side fragments of tile rows [0, r1): frag[0..5] as gram_fragments, frag[6..7] =
@@ -141,7 +151,7 @@ __device__ __forceinline__ void gram_rhs_fragments(const unsigned char* tile, co
 }
 
 template <int LD, int MAXM, bool USER>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(WarpBlockSmem<LD, MAXM>::kMaxWarps * 32, 1)
 cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count) {
   extern __shared__ __align__(128) unsigned char smem[];
   using Sm = WarpBlockSmem<LD, MAXM>;
@@ -149,12 +159,16 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
   const int wpb = blockDim.x >> 5;
 
   // the S cache of the other side, resident in shared memory for the CTA's lifetime
-  const double* Sp = a.S;
+  const double* S_s = reinterpret_cast<const double*>(smem);
   if (Sm::kSInSmem) {
-    double* S_s = reinterpret_cast<double*>(smem);
-    for (int t = threadIdx.x; t < LD * LD / 2; t += blockDim.x)
-      reinterpret_cast<double2*>(S_s)[t] = __ldg(reinterpret_cast<const double2*>(a.S) + t);
-    Sp = S_s;
+    double* S_w = reinterpret_cast<double*>(smem);
+    for (int t = threadIdx.x; t < s_tri(Sm::kNB, 0) * 256; t += blockDim.x) {
+      const int blk = t >> 8, r = (t >> 4) & 15, c = t & 15;
+      int bi = 0;
+      while (s_tri(bi + 1, 0) <= blk) bi++;
+      const int bj = blk - s_tri(bi, 0);
+      S_w[blk * kSBlk + r * 17 + c] = __ldg(a.S + (size_t)(bi * 16 + r) * LD + bj * 16 + c);
+    }
     __syncthreads();
   }
 
@@ -172,34 +186,85 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
   const int nblocks = (K + kFB - 1) / kFB;
   const int f = lane & 15, hh = lane >> 4;
 
-  for (int slot = blockIdx.x * wpb + warp; slot < count; slot += gridDim.x * wpb) {
-    const int row = order[first + slot];
-    const int64_t p0 = a.ptr[row];
-    const int n = (int)(a.ptr[row + 1] - p0);
+  // Descriptor of the NEXT row, fetched in four dependent steps (order -> offsets -> indices ->
+  // weights) spread over the factor blocks of the current row: measured on rows of 65..128 nonzeros
+  // (profiles r01g) a warp spent ~15 % of its time stalled on exactly this chain at every row start.
+  constexpr int XN = (LD + 31) / 32;
+  const int stride = gridDim.x * wpb;
+  int row_n = 0, n_n = 0, id_n[MAXM];
+  int64_t p0_n = 0, p1_n = 0;
+  double wi_n[MAXM], pc_n[MAXM], wi_row_n = 0.0, x_n[XN];
+  uint32_t g_n[MAXM];
+#pragma unroll
+  for (int m = 0; m < MAXM; m++) { id_n[m] = 0; wi_n[m] = 0.0; pc_n[m] = 0.0; g_n[m] = 0; }
+#pragma unroll
+  for (int i = 0; i < XN; i++) x_n[i] = 0.0;
+  auto fetch_next = [&](int stage, int slot_n) {
+    if (slot_n >= count) return;
+    if (stage == 0) {
+      row_n = order[first + slot_n];
+    } else if (stage == 1) {
+      p0_n = a.ptr[row_n];
+      p1_n = a.ptr[row_n + 1];
+      const double* xr = a.X + (size_t)(a.row_base + row_n) * LD;
+#pragma unroll
+      for (int i = 0; i < XN; i++)
+        if (lane + 32 * i < LD) x_n[i] = xr[lane + 32 * i];
+      if (!USER) wi_row_n = a.Wi[a.row_base + row_n];
+    } else if (stage == 2) {
+      n_n = (int)(p1_n - p0_n);
+#pragma unroll
+      for (int m = 0; m < MAXM; m++) {
+        const int j = m * 32 + lane;
+        if (j < n_n) {
+          id_n[m] = a.idx[p0_n + j];
+          if (a.use_cache) pc_n[m] = a.pc_in[p0_n + j];
+          if (a.pc_out.n) g_n[m] = a.pc_map[p0_n + j];
+        }
+      }
+    } else if (USER) {
+#pragma unroll
+      for (int m = 0; m < MAXM; m++)
+        if (m * 32 + lane < n_n) wi_n[m] = a.Wi[id_n[m]];
+    }
+  };
+  {
+    const int slot0 = blockIdx.x * wpb + warp;
+#pragma unroll
+    for (int st = 0; st < 4; st++) fetch_next(st, slot0);
+  }
+
+  for (int slot = blockIdx.x * wpb + warp; slot < count; slot += stride) {
+    const int row = row_n;
+    const int64_t p0 = p0_n;
+    const int n = n_n;
     const int n_pad = (n + 3) & ~3;
     const int grow = a.row_base + row;
-    double* xrow = a.X + (size_t)grow * LD;
-    const double wi_row = USER ? 0.0 : a.Wi[grow];
+    const double wi_row = USER ? 0.0 : wi_row_n;
     const double g = USER ? 1.0 : wi_row;
 
     double pr[MAXM], cw[MAXM], wr[MAXM];
+    uint32_t gpos[MAXM];
 #pragma unroll
     for (int m = 0; m < MAXM; m++) {
       const int j = m * 32 + lane;
       pr[m] = 0.0; cw[m] = 0.0; wr[m] = 0.0;
+      gpos[m] = g_n[m];
       if (j < n) {
-        const int id = a.idx[p0 + j];
-        rowp_s[j] = a.Y + (size_t)id * LD;
+        rowp_s[j] = a.Y + (size_t)id_n[m] * LD;
         const double w = a.val ? a.val[p0 + j] : 1.0;
         wr[m] = w * w;
-        cw[m] = w - (USER ? a.Wi[id] : wi_row);
-        if (a.use_cache) pr[m] = a.pc_in[p0 + j];
+        cw[m] = w - (USER ? wi_n[m] : wi_row);
+        if (a.use_cache) pr[m] = pc_n[m];
       }
       c_s[j] = cw[m];
       z_s[j] = 0.0;
     }
-    for (int k = lane; k < LD; k += 32) x_s[k] = xrow[k];
+#pragma unroll
+    for (int i = 0; i < XN; i++)
+      if (lane + 32 * i < LD) x_s[lane + 32 * i] = x_n[i];
     __syncwarp();
+    const int stages_in_loop = nblocks < 4 ? nblocks : 4;
 
     if (!a.use_cache) {   // prediction cache from scratch: p_j = <x, y_j>
       for (int fb = 0; fb < nblocks; fb++) {
@@ -227,25 +292,58 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
     cp_async_commit();
     for (int fb = 0; fb < nblocks; fb++) {
       const int f0 = fb * kFB;
+      if (fb < 4) fetch_next(fb, slot + stride);
 #pragma unroll
       for (int m = 0; m < MAXM; m++) {
         const int j = m * 32 + lane;
         if (j < n) z_s[j] = wr[m] - cw[m] * pr[m];
       }
-      // S.x for this block while the tile is in flight: t_f = sum_k x_k S[k][f0+f]
+      // S.x for this block while the tile is in flight: t_f = sum_k x_k S[k][f0+f]; lane = (f, half
+      // of the k blocks)
       double tsum;
-      {
-        const double* __restrict__ Sc = Sp + (size_t)(hh * (LD / 2)) * LD + f0 + f;
-        const double* __restrict__ xh = x_s + hh * (LD / 2);
+      if (Sm::kSInSmem) {
         double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;   // four independent chains
+        const int kb0 = (Sm::kNB * hh) / 2, kb1 = (Sm::kNB * (hh + 1)) / 2;
+        for (int kb = kb0; kb < kb1; kb++) {
+          const double* __restrict__ xk = x_s + kb * 16;
+          if (kb <= fb) {   // S[f0+f][16 kb + kk]: row f of block (fb, kb)
+            const double* __restrict__ sb = S_s + s_tri(fb, kb) * kSBlk + f * 17;
+#pragma unroll
+            for (int kk = 0; kk < 16; kk += 4) {
+              const double2 xa = *reinterpret_cast<const double2*>(xk + kk);
+              const double2 xb = *reinterpret_cast<const double2*>(xk + kk + 2);
+              t0 += xa.x * sb[kk];
+              t1 += xa.y * sb[kk + 1];
+              t2 += xb.x * sb[kk + 2];
+              t3 += xb.y * sb[kk + 3];
+            }
+          } else {          // S[16 kb + kk][f0+f]: column f of block (kb, fb)
+            const double* __restrict__ sb = S_s + s_tri(kb, fb) * kSBlk + f;
+#pragma unroll
+            for (int kk = 0; kk < 16; kk += 4) {
+              const double2 xa = *reinterpret_cast<const double2*>(xk + kk);
+              const double2 xb = *reinterpret_cast<const double2*>(xk + kk + 2);
+              t0 += xa.x * sb[kk * 17];
+              t1 += xa.y * sb[(kk + 1) * 17];
+              t2 += xb.x * sb[(kk + 2) * 17];
+              t3 += xb.y * sb[(kk + 3) * 17];
+            }
+          }
+        }
+        tsum = (t0 + t1) + (t2 + t3);
+        tsum += __shfl_xor_sync(kFullMask, tsum, 16);
+      } else {
+        const double* __restrict__ Sc = a.S + (size_t)(hh * (LD / 2)) * LD + f0 + f;
+        const double* __restrict__ xh = x_s + hh * (LD / 2);
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll 2
         for (int k = 0; k < LD / 2; k += 4) {
           const double2 xa = *reinterpret_cast<const double2*>(xh + k);
           const double2 xb = *reinterpret_cast<const double2*>(xh + k + 2);
-          t0 += xa.x * Sc[(size_t)k * LD];
-          t1 += xa.y * Sc[(size_t)(k + 1) * LD];
-          t2 += xb.x * Sc[(size_t)(k + 2) * LD];
-          t3 += xb.y * Sc[(size_t)(k + 3) * LD];
+          t0 += xa.x * __ldg(Sc + (size_t)k * LD);
+          t1 += xa.y * __ldg(Sc + (size_t)(k + 1) * LD);
+          t2 += xb.x * __ldg(Sc + (size_t)(k + 2) * LD);
+          t3 += xb.y * __ldg(Sc + (size_t)(k + 3) * LD);
         }
         tsum = (t0 + t1) + (t2 + t3);
         tsum += __shfl_xor_sync(kFullMask, tsum, 16);
@@ -263,7 +361,9 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
           int rw = lane >> 2, cl = 2 * (lane & 3) + ii;
           if (t >= 1) rw += 8;
           if (t == 2) cl += 8;
-          const double v = frag[2 * t + ii] + g * Sp[(size_t)(f0 + rw) * LD + f0 + cl];
+          const double sbb = Sm::kSInSmem ? S_s[s_tri(fb, fb) * kSBlk + rw * 17 + cl]
+                                          : __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
+          const double v = frag[2 * t + ii] + g * sbb;
           Gs[rw * 16 + cl] = v;
           if (t == 1) Gs[cl * 16 + rw] = v;
         }
@@ -327,9 +427,10 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 #pragma unroll
       for (int m = 0; m < MAXM; m++) {
         const int j = m * 32 + lane;
-        if (j < n) pc_store(a, p0 + j, pr[m]);
+        if (j < n) pc_store_at(a, gpos[m], pr[m]);
       }
     }
+    for (int st = stages_in_loop; st < 4; st++) fetch_next(st, slot + stride);   // K < 64: finish the chain here
     __syncwarp();
   }
 }
@@ -557,6 +658,222 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Team kernel, second version: one CTA (TW = 2, 4, 8 or 16 warps) per row of up to 32*TW nonzeros,
+// ONE nonzero per thread.
+//
+// What the first version paid per factor block was a full memory round trip: the tile of block
+// fb + 1 could only be requested after the prediction-cache update of block fb had read the tile of
+// block fb again.  Here every thread copies its own nonzero's 16 values of the block into registers
+// when the tile arrives, so the tile buffer is free as soon as the tensor-core pass over it is done
+// and the gather of the next block runs underneath the cross-warp reduction, the 16-step solve and
+// the cache update (prefetch distance ~1000+ cycles, no second tile buffer).
+// ---------------------------------------------------------------------------------------------
+template <int LD, int TW>
+struct TeamSmem {
+  static constexpr int kT = TW * 32;
+  static constexpr int kParts = (kT / 16 < LD / 2) ? kT / 16 : LD / 2;   // S.x: threads = (factor, slice of k)
+  static constexpr size_t kTile = (size_t)kT * 128;
+  static constexpr size_t kBytes = kTile + (size_t)kT * (8 + 8 + 8) + (size_t)LD * 8 + (size_t)TW * kPartLen * 8 +
+                                   (256 + 16 + 16 + 16 + kParts * 16) * 8;
+};
+
+template <int LD, int TW, bool USER>
+__global__ void __launch_bounds__(TW * 32, (TW <= 8 ? 16 / TW : 1))
+cd_team_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using Sm = TeamSmem<LD, TW>;
+  constexpr int kT = Sm::kT;
+  constexpr int kParts = Sm::kParts;
+  constexpr int kPer = LD / kParts;                       // k's per S.x thread (>= 2)
+  constexpr int kRedItems = kPartLen + 16;                // 208 partial sums + 16 S.x totals
+  constexpr int kRedIter = (kRedItems + kT - 1) / kT;
+  unsigned char* tile = smem;
+  const double** rowp_s = reinterpret_cast<const double**>(smem + Sm::kTile);
+  double* c_s = reinterpret_cast<double*>(smem + Sm::kTile + (size_t)kT * 8);
+  double* z_s = c_s + kT;
+  double* x_s = z_s + kT;
+  double* slots = x_s + LD;
+  double* Gs = slots + TW * kPartLen;
+  double* Pt = Gs + 256;
+  double* Tt = Pt + 16;
+  double* delta_s = Tt + 16;
+  double* tpart = delta_s + 16;    // [kParts][16 factors]
+
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const int row = order[first + blockIdx.x];
+  const int64_t p0 = a.ptr[row];
+  const int n = (int)(a.ptr[row + 1] - p0);
+  const int n_pad = (n + 3) & ~3;
+  const int grow = a.row_base + row;
+  double* xrow = a.X + (size_t)grow * LD;
+  const int K = a.K;
+  const double wi_row = USER ? 0.0 : a.Wi[grow];
+  const double g = USER ? 1.0 : wi_row;
+  const bool mine = tid < n;
+
+  double pr = 0.0, cw = 0.0, wr = 0.0;
+  if (mine) {
+    const int id = a.idx[p0 + tid];
+    rowp_s[tid] = a.Y + (size_t)id * LD;
+    const double w = a.val ? a.val[p0 + tid] : 1.0;
+    wr = w * w;
+    cw = w - (USER ? a.Wi[id] : wi_row);
+    if (a.use_cache) pr = a.pc_in[p0 + tid];
+  }
+  c_s[tid] = cw;
+  z_s[tid] = 0.0;
+  for (int k = tid; k < LD; k += kT) x_s[k] = xrow[k];
+  __syncthreads();
+
+  if (!a.use_cache) {
+    // prediction cache from scratch, p_j = <x, y_j>: 8 lanes per nonzero straight from global memory
+    // (whole 128-byte lines per 8 lanes, all loads of a thread independent)
+    const int g8 = tid >> 3, gl = tid & 7;
+    for (int j0 = 0; j0 < n; j0 += kT / 8) {
+      const int j = j0 + g8;
+      double acc0 = 0.0, acc1 = 0.0;
+      if (j < n) {
+        const double* yrow = rowp_s[j];
+#pragma unroll
+        for (int c = 0; c < LD; c += kFB) {
+          const double2 d = ldg2(yrow + c + gl * 2);
+          acc0 += x_s[c + gl * 2] * d.x;
+          acc1 += x_s[c + gl * 2 + 1] * d.y;
+        }
+      }
+      double acc = acc0 + acc1;
+      acc += __shfl_xor_sync(kFullMask, acc, 1);
+      acc += __shfl_xor_sync(kFullMask, acc, 2);
+      acc += __shfl_xor_sync(kFullMask, acc, 4);
+      if (j < n && gl == 0) z_s[j] = acc;
+    }
+    __syncthreads();
+    if (mine) pr = z_s[tid];
+    __syncthreads();
+  }
+
+  const int nblocks = (K + kFB - 1) / kFB;
+  const int w_r0 = warp * 32, w_r1 = min(warp * 32 + 32, n_pad);
+  const int tf = tid & 15, tpart_id = tid >> 4;
+
+  stage_tile_rows(tile, rowp_s, n, n_pad, 0, tid, kT);
+  cp_async_commit();
+  for (int fb = 0; fb < nblocks; fb++) {
+    const int f0 = fb * kFB;
+    if (mine) z_s[tid] = wr - cw * pr;
+    if (tpart_id < kParts) {   // partial t_f = sum over this thread's k's of x_k S[k][f0+f] (S symmetric)
+      const double* __restrict__ Sc = a.S + (size_t)(tpart_id * kPer) * LD + f0 + tf;
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kPer; k += 2) {
+        t0 += x_s[tpart_id * kPer + k] * __ldg(Sc + (size_t)k * LD);
+        t1 += x_s[tpart_id * kPer + k + 1] * __ldg(Sc + (size_t)(k + 1) * LD);
+      }
+      tpart[tpart_id * 16 + tf] = t0 + t1;
+    }
+    // the S_BB entries the reduction adds: requested now, consumed after the tensor-core pass
+    double s_bb[kRedIter];
+#pragma unroll
+    for (int q = 0; q < kRedIter; q++) {
+      const int i = tid + q * kT;
+      s_bb[q] = 0.0;
+      if (i < 192) {
+        const int t = i >> 6, l = (i & 63) >> 1, ii = i & 1;
+        int rw = l >> 2, cl = 2 * (l & 3) + ii;
+        if (t >= 1) rw += 8;
+        if (t == 2) cl += 8;
+        s_bb[q] = __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    double y[16];
+    if (mine) load_tile_row(tile, tid, y);
+    double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    gram_rhs_fragments(tile, c_s, z_s, w_r0, w_r1, frag);
+    double* slot = slots + warp * kPartLen;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      slot[t * 64 + lane * 2] = frag[2 * t];
+      slot[t * 64 + lane * 2 + 1] = frag[2 * t + 1];
+    }
+    if ((lane & 3) == 0) {
+      slot[192 + (lane >> 2)] = frag[6];
+      slot[200 + (lane >> 2)] = frag[8];
+    }
+    __syncthreads();
+    if (fb + 1 < nblocks) {   // the tile is consumed: fetch the next block underneath the solve
+      stage_tile_rows(tile, rowp_s, n, n_pad, fb + 1, tid, kT);
+      cp_async_commit();
+    }
+#pragma unroll
+    for (int q = 0; q < kRedIter; q++) {
+      const int i = tid + q * kT;
+      if (i < kPartLen) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TW; w++) s += slots[w * kPartLen + i];
+        if (i < 192) {   // H = G + g S_BB
+          const int t = i >> 6, l = (i & 63) >> 1, ii = i & 1;
+          int rw = l >> 2, cl = 2 * (l & 3) + ii;
+          if (t >= 1) rw += 8;
+          if (t == 2) cl += 8;
+          s += g * s_bb[q];
+          Gs[rw * 16 + cl] = s;
+          if (t == 1) Gs[cl * 16 + rw] = s;
+        } else {
+          Pt[i - 192] = s;
+        }
+      } else if (i < kRedItems) {
+        const int ff = i - kPartLen;
+        double s = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < kParts; q2++) s += tpart[q2 * 16 + ff];
+        Tt[ff] = s;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int ff = lane & 15;
+      double h[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + ff];
+      const double hff = Gs[ff * 16 + ff];
+      const double xf = x_s[f0 + ff];
+      double numer = Pt[ff] - g * Tt[ff] + xf * hff;
+      const double rden = 1.0 / (hff + a.reg);
+#pragma unroll
+      for (int sidx = 0; sidx < 16; sidx++) {
+        const double d = numer * rden - xf;
+        const double ds = __shfl_sync(kFullMask, d, sidx);
+        if (ff > sidx) numer -= ds * h[sidx];
+      }
+      const double xnew = numer * rden;
+      if (lane < 16) {
+        const bool livef = f0 + ff < K;
+        if (livef) x_s[f0 + ff] = xnew;
+        delta_s[ff] = livef ? xnew - xf : 0.0;
+      }
+    }
+    __syncthreads();
+    if (mine) {
+      double a0 = pr, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        a0 += delta_s[e] * y[e];
+        a1 += delta_s[e + 1] * y[e + 1];
+        a2 += delta_s[e + 2] * y[e + 2];
+        a3 += delta_s[e + 3] * y[e + 3];
+      }
+      pr = (a0 + a1) + (a2 + a3);
+    }
+  }
+  for (int k = tid; k < K; k += kT) store_row_value(a, (size_t)grow * LD + k, x_s[k]);
+  if (a.pc_out.n && mine) pc_store(a, p0 + tid, pr);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Heavy rows: slabs of kSlab nonzeros, prediction cache in HBM (a compact array per side), one
 // launch pair per factor block over a BATCH of rows small enough that the block's lines stay in L2
 // between the partials launch and the deferred cache update of the next one.
@@ -570,6 +887,17 @@ struct HeavyUnits {
   const int32_t* hrow_id;      // owned-row id of heavy row h
   const int32_t* hrow_unit0;   // first unit of heavy row h
   const int32_t* hrow_units;   // number of units of heavy row h
+  const int32_t* hrow_grp0;    // first reduction group of heavy row h (groups of <= 32 consecutive units)
+  const int32_t* hrow_grps;    // number of groups of heavy row h
+  const int32_t* grp_unit0;    // first unit of group g
+  const int32_t* grp_cnt;      // units in group g
+  // Launch order of a batch's units (nullptr: canonical order).  Canonical order is row by row; the
+  // launch order sorts the slabs by the id of their FIRST neighbour, so that CTAs running at the same
+  // time gather (largely) the same neighbour rows: with every heavy row of a side in one batch, a
+  // neighbour's line is then fetched from HBM once per step and served to the other slabs from L2,
+  // instead of once per slab and again for the deferred cache update (measured before: 243 B of
+  // DRAM reads per nonzero and block, L2 hit rate 9 %; profiles/README.md r01f).
+  const int32_t* launch;
 };
 
 // p_j = <x_row, y_j> for every nonzero of the units [u0, u0 + gridDim.x): 8 lanes per nonzero.
@@ -578,7 +906,7 @@ __global__ void __launch_bounds__(kBlkThreads)
 heavy_pred_kernel(CdSide a, HeavyUnits hu, int u0, double* __restrict__ pred) {
   __shared__ double x_s[LD];
   const int tid = threadIdx.x;
-  const int u = u0 + blockIdx.x;
+  const int u = hu.launch ? hu.launch[blockIdx.x] : u0 + blockIdx.x;
   const int row = hu.unit_row[u];
   const double* xrow = a.X + (size_t)(a.row_base + row) * LD;
   for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
@@ -633,7 +961,7 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   static_assert(kSlab == kBlkThreads, "one nonzero per thread");
 
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-  const int u = u0 + blockIdx.x;
+  const int u = hu.launch ? hu.launch[blockIdx.x] : u0 + blockIdx.x;
   const int row = hu.unit_row[u];
   const int64_t off = hu.unit_off[u], poff = hu.unit_poff[u];
   const int n = hu.unit_cnt[u];
@@ -709,12 +1037,14 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   }
 }
 
-// Level-2 reduction for rows with very many units: out[g] = sum of the 32 unit partials of group g.
+// Level-1 reduction: out[g - g0] = sum of the unit partials of group g (<= 32 consecutive units of one
+// row), added in unit order.
 __global__ void __launch_bounds__(kBlkThreads)
-heavy_reduce_kernel(const double* __restrict__ partials, int nu, double* __restrict__ out) {
+heavy_reduce_kernel(const double* __restrict__ partials, HeavyUnits hu, int g0, int u0, double* __restrict__ out) {
   const int tid = threadIdx.x;
   if (tid >= kPartLen) return;
-  const int q0 = blockIdx.x * 32, q1 = min(q0 + 32, nu);
+  const int g = g0 + blockIdx.x;
+  const int q0 = hu.grp_unit0[g] - u0, q1 = q0 + hu.grp_cnt[g];
   double s = 0.0;
   for (int q = q0; q < q1; q++) s += partials[(size_t)q * kPartLen + tid];
   out[(size_t)blockIdx.x * kPartLen + tid] = s;
@@ -723,11 +1053,11 @@ heavy_reduce_kernel(const double* __restrict__ partials, int nu, double* __restr
 // One CTA per heavy row of the batch: add the row's partials in a fixed order (8 warps take every
 // 8th entry, then the 8 sums are added in warp order) while all threads form S.x of the block;
 // warp 0 then runs the 16-step recurrence; the new factors and d_f go to HBM.
-// override_count > 0: the row's partials are partials[0 .. override_count) (level-2 groups).
+// partials = the group sums of the batch (heavy_reduce_kernel), group g at slot g - g0.
 template <int LD, bool USER>
 __global__ void __launch_bounds__(kBlkThreads)
-heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int u0, int fb, const double* __restrict__ partials,
-                   int override_count, double* __restrict__ delta) {
+heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int g0, int fb, const double* __restrict__ partials,
+                   double* __restrict__ delta) {
   __shared__ double x_s[LD];
   __shared__ double Gs[256];
   __shared__ double Pt[16];
@@ -742,8 +1072,8 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int u0, int fb, const double
   const double g = USER ? 1.0 : a.Wi[grow];
   double* xrow = a.X + (size_t)grow * LD;
   for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
-  const int ufirst = override_count > 0 ? 0 : hu.hrow_unit0[h] - u0;
-  const int ucount = override_count > 0 ? override_count : hu.hrow_units[h];
+  const int ufirst = hu.hrow_grp0[h] - g0;
+  const int ucount = hu.hrow_grps[h];
   {
     double acc[7];
 #pragma unroll

@@ -70,6 +70,14 @@ __device__ __forceinline__ void store_row_value(const CdSide& a, size_t off, dou
   for (int p = 0; p < a.peers.n; p++) a.peers.x[p][off] = v;
 }
 
+// Store a prediction at global position g of the other orientation's cache (on whichever rank holds it).
+__device__ __forceinline__ void pc_store_at(const CdSide& a, uint32_t g, double v) {
+  int r = 0;
+#pragma unroll
+  for (int t = 1; t < 8; t++) r += (t < a.pc_out.n && g >= a.pc_out.bound[t]) ? 1 : 0;
+  a.pc_out.base[r][g - a.pc_out.bound[r]] = v;
+}
+
 __device__ __forceinline__ void pc_store(const CdSide& a, int64_t local_pos, double v) {
   const uint32_t g = a.pc_map[local_pos];
   int r = 0;

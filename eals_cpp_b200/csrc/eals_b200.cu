@@ -16,8 +16,11 @@
 #include <cstring>
 #include <new>
 #include <random>
+#include <thread>
 #include <utility>
 #include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "cd_block.cuh"
 #include "cd_sweep.cuh"
@@ -66,6 +69,20 @@ struct StageTimer {
   }
 };
 
+// Host-side helper: fn(thread, begin, end) over [0, n) in contiguous chunks on up to 16 threads.
+template <typename F>
+void parallel_chunks(int64_t n, int* n_threads_out, F fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, 16u)), std::max<int64_t>(1, n / 65536));
+  if (n_threads_out) *n_threads_out = T;
+  if (T <= 1) { fn(0, (int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  const int64_t per = (n + T - 1) / T;
+  for (int t = 0; t < T; t++) th.emplace_back(fn, t, std::min(n, t * per), std::min(n, (t + 1) * per));
+  for (auto& x : th) x.join();
+}
+constexpr int kMaxHostThreads = 16;
+
 template <typename T>
 int dev_alloc(T** p, size_t n) {
   *p = nullptr;
@@ -99,7 +116,10 @@ constexpr int kMidBucket = 4;     // first one-CTA-per-row bucket
 constexpr int kHeavyBucket = 7;
 // Heavy rows per launch group.  Measured on c4 (profiles/README.md r01b): launch granularity matters
 // more than keeping one factor block of the batch L2-resident (384k nnz: 363 ms, 24M nnz: 204 ms).
-constexpr int64_t kDefaultBatchNnz = 24 * 1024 * 1024;
+// Since the slabs of a batch are launched in neighbour order (HeavyUnits::launch) the bigger the batch
+// the more slabs share a gathered line while it is in L2, so by default ALL heavy rows of a side form
+// one batch (the limit only bounds the partials scratch: 6.5 bytes per nonzero).
+constexpr int64_t kDefaultBatchNnz = 4LL * 1024 * 1024 * 1024;
 
 struct HeavyBatch { int h0, h1, u0, u1; };
 
@@ -118,6 +138,10 @@ struct Side {
   int32_t *unit_row = nullptr, *unit_hrow = nullptr, *unit_cnt = nullptr;
   int64_t *unit_off = nullptr, *unit_poff = nullptr;
   int32_t *hrow_id = nullptr, *hrow_unit0 = nullptr, *hrow_units = nullptr;
+  int32_t *hrow_grp0 = nullptr, *hrow_grps = nullptr, *grp_unit0 = nullptr, *grp_cnt = nullptr;
+  int32_t* unit_launch = nullptr;     // launch order of the canonical batches (see HeavyUnits::launch)
+  int n_groups = 0;
+  std::vector<int32_t> h_hrow_grp0, h_hrow_grps;
   std::vector<int32_t> h_hrow_unit0, h_hrow_units;
   std::vector<int32_t> h_row_to_hrow;  // owned row -> heavy index or -1 (only filled when heavy rows exist)
   std::vector<HeavyBatch> batches;
@@ -126,7 +150,7 @@ struct Side {
   // capacities (elements) of the device arrays above, see dev_reserve
   size_t cap_ptr = 0, cap_idx = 0, cap_val = 0, cap_order = 0, cap_unit_row = 0, cap_unit_hrow = 0, cap_unit_cnt = 0,
          cap_unit_off = 0, cap_unit_poff = 0, cap_hrow_id = 0, cap_hrow_unit0 = 0, cap_hrow_units = 0, cap_pred = 0,
-         cap_delta = 0;
+         cap_delta = 0, cap_hrow_grp0 = 0, cap_hrow_grps = 0, cap_grp_unit0 = 0, cap_grp_cnt = 0, cap_unit_launch = 0;
   std::vector<int64_t> h_ptr;         // host copy of ptr (rebased to 0)
 };
 
@@ -197,6 +221,7 @@ void free_side(Side& s) {
   cudaFree(s.pred); cudaFree(s.delta);
   cudaFree(s.unit_row); cudaFree(s.unit_hrow); cudaFree(s.unit_cnt); cudaFree(s.unit_off); cudaFree(s.unit_poff);
   cudaFree(s.hrow_id); cudaFree(s.hrow_unit0); cudaFree(s.hrow_units);
+  cudaFree(s.hrow_grp0); cudaFree(s.hrow_grps); cudaFree(s.grp_unit0); cudaFree(s.grp_cnt); cudaFree(s.unit_launch);
   s = Side();
 }
 
@@ -227,25 +252,32 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ ptr, const int32
 
 int ensure_partials(eals_model* m, size_t n);
 
-// For every nonzero of the local slice of orientation A (rows [a0, a0 + rowsA), offsets rebased to
-// 0): the GLOBAL position of the same nonzero in orientation B (full offsets/indices).
-__global__ void build_map_kernel(const int64_t* __restrict__ ptrA, const int32_t* __restrict__ idxA, int rowsA, int a0,
-                                 const int64_t* __restrict__ ptrB_full, const int32_t* __restrict__ idxB_full,
-                                 int64_t nnzA, uint32_t* __restrict__ map) {
+// Both position maps in one pass over the FULL CSC arrays, one thread per nonzero q: its column i
+// (search in the offsets; neighbouring threads walk the same path), its user u = row_idx[q] and the
+// CSR position p of (u, i) — a search inside the SHORT row u instead of inside a column that may
+// hold millions of entries.  map_i[q] = p for the owned items, map_u[p] = q for the owned users.
+__global__ void build_maps_kernel(const int64_t* __restrict__ cp, const int32_t* __restrict__ ri, int N,
+                                  const int64_t* __restrict__ rp, const int32_t* __restrict__ ci, int64_t nnz,
+                                  int ub, int ue, int64_t rp_ub, uint32_t* __restrict__ map_u,
+                                  int ib, int ie, int64_t cp_ib, uint32_t* __restrict__ map_i, int* __restrict__ bad) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nnzA) return;
-  int lo = 0, hi = rowsA;                   // largest local row with ptrA[row] <= q
+  if (q >= nnz) return;
+  int lo = 0, hi = N;                       // largest i with cp[i] <= q
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if (ptrA[mid] <= q) lo = mid; else hi = mid;
+    if (cp[mid] <= q) lo = mid; else hi = mid;
   }
-  const int r = a0 + lo, c = idxA[q];
-  int64_t a = ptrB_full[c], b = ptrB_full[c + 1];
+  const int i = lo, u = ri[q];
+  const bool own_u = u >= ub && u < ue, own_i = i >= ib && i < ie;
+  if (!own_u && !own_i) return;
+  int64_t a = rp[u], b = rp[u + 1];
   while (b - a > 1) {
     const int64_t mid = (a + b) >> 1;
-    if (idxB_full[mid] <= r) a = mid; else b = mid;
+    if (ci[mid] <= i) a = mid; else b = mid;
   }
-  map[q] = (b > a && idxB_full[a] == r) ? (uint32_t)a : 0xffffffffu;
+  if (!(b > a && ci[a] == i)) { atomicExch(bad, 1); return; }
+  if (own_i) map_i[q - cp_ib] = (uint32_t)a;
+  if (own_u) map_u[a - rp_ub] = (uint32_t)q;
 }
 
 __global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz, int* __restrict__ bad) {
@@ -313,18 +345,17 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   OK(dev_reserve(&m->pc_i, &m->cap_pc_i, (size_t)ni));
   OK(dev_reserve(&m->map_u, &m->cap_map_u, (size_t)nu));
   OK(dev_reserve(&m->map_i, &m->cap_map_i, (size_t)ni));
-  build_map_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, m->stream>>>(m->users.ptr, m->users.idx, m->users.rows, m->ub,
-                                                                       d_cp, d_ri, nu, m->map_u);
-  OK(check_launch(m));
-  build_map_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, m->stream>>>(m->items.ptr, m->items.idx, m->items.rows, m->ib,
-                                                                       d_rp, d_ci, ni, m->map_i);
-  OK(check_launch(m));
   int* bad;
   OK(dev_alloc(&bad, 1));
   CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
+  CU(cudaMemsetAsync(m->map_u, 0xff, sizeof(uint32_t) * (size_t)nu, m->stream));   // unreached CSR entries stay invalid
+  {
+    const int me_ = single ? 0 : m->rank;
+    build_maps_kernel<<<(unsigned)((nnz_total + 255) / 256), 256, 0, m->stream>>>(
+        d_cp, d_ri, m->N, d_rp, d_ci, nnz_total, m->ub, m->ue, rp[me_], m->map_u, m->ib, m->ie, cp[me_], m->map_i, bad);
+    OK(check_launch(m));
+  }
   check_perm_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, m->stream>>>(m->map_u, nu, bad);
-  OK(check_launch(m));
-  check_perm_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, m->stream>>>(m->map_i, ni, bad);
   OK(check_launch(m));
   int h_bad = 0;
   CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -348,25 +379,73 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   return EALS_OK;
 }
 
+__global__ void unit_key_kernel(const int32_t* __restrict__ idx, const int64_t* __restrict__ unit_off, int u0, int n,
+                                uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  keys[t] = (uint32_t)idx[unit_off[u0 + t]];
+  vals[t] = u0 + t;
+}
+
+// Launch order of every canonical batch: its slabs sorted by the id of their first neighbour.
+int build_launch_order(eals_model* m, Side& s) {
+  OK(dev_reserve(&s.unit_launch, &s.cap_unit_launch, (size_t)std::max(s.n_units, 1)));
+  if (s.n_units == 0) return EALS_OK;
+  uint32_t *keys = nullptr, *keys_out = nullptr;
+  int32_t* vals = nullptr;
+  void* tmp = nullptr;
+  int rc = EALS_OK;
+  auto done = [&](int code) { cudaFree(keys); cudaFree(keys_out); cudaFree(vals); cudaFree(tmp); return code; };
+  if ((rc = dev_alloc(&keys, (size_t)s.max_batch_units)) != EALS_OK) return done(rc);
+  if ((rc = dev_alloc(&keys_out, (size_t)s.max_batch_units)) != EALS_OK) return done(rc);
+  if ((rc = dev_alloc(&vals, (size_t)s.max_batch_units)) != EALS_OK) return done(rc);
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, s.unit_launch, s.max_batch_units, 0, 32, m->stream);
+  if (cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)) != cudaSuccess) return done(fail(EALS_ERR_ALLOC, "scratch for the slab sort"));
+  for (const HeavyBatch& b : s.batches) {
+    const int n = b.u1 - b.u0;
+    unit_key_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(s.idx, s.unit_off, b.u0, n, keys, vals);
+    if (cudaGetLastError() != cudaSuccess) return done(fail(EALS_ERR_CUDA, "unit_key_kernel launch"));
+    if (cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, s.unit_launch + b.u0, n, 0, 32, m->stream) != cudaSuccess)
+      return done(fail(EALS_ERR_CUDA, "slab sort"));
+  }
+  if (cudaStreamSynchronize(m->stream) != cudaSuccess) return done(fail(EALS_ERR_CUDA, "slab sort sync"));
+  return done(EALS_OK);
+}
+
 // Upload the owned slice [begin, end) of one orientation of the matrix and bucket its rows.
 int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int space,
                const int64_t* ptr_full, const int32_t* idx_full, const double* val_full) {
   StageTimer tm;
   s.rows = end - begin;
   s.row_base = begin;
-  s.h_ptr.assign((size_t)s.rows + 1, 0);
+  s.h_ptr.resize((size_t)s.rows + 1);
+  if (s.rows == 0) s.h_ptr[0] = 0;
+  int64_t base = 0;   // offset of the slice's first nonzero in the full index arrays
   if (s.rows > 0) {
+    std::vector<int64_t> raw;
     if (space == EALS_DEVICE) {
-      CU(cudaMemcpy(s.h_ptr.data(), ptr_full + begin, sizeof(int64_t) * (s.rows + 1), cudaMemcpyDeviceToHost));
-    } else {
-      std::memcpy(s.h_ptr.data(), ptr_full + begin, sizeof(int64_t) * (s.rows + 1));
+      raw.resize((size_t)s.rows + 1);
+      CU(cudaMemcpy(raw.data(), ptr_full + begin, sizeof(int64_t) * (s.rows + 1), cudaMemcpyDeviceToHost));
     }
+    const int64_t* src = space == EALS_DEVICE ? raw.data() : ptr_full + begin;
+    base = src[0];
+    int bad_row[kMaxHostThreads];
+    for (int& b : bad_row) b = -1;
+    int64_t* dst = s.h_ptr.data();
+    // copy + rebase + check, chunked over host threads (10M offsets: 30 ms -> a few ms)
+    parallel_chunks((int64_t)s.rows + 1, nullptr, [&](int t, int64_t b0, int64_t b1) {
+      for (int64_t r = b0; r < b1; r++) {
+        if (r < s.rows) {
+          const int64_t len = src[r + 1] - src[r];
+          if ((len < 0 || len > other_dim) && bad_row[t] < 0) bad_row[t] = (int)r;
+        }
+        dst[r] = src[r] - base;
+      }
+    });
+    for (int b : bad_row)
+      if (b >= 0) return fail(EALS_ERR_ARG, "offsets not monotone / row longer than the other dimension at row %d", begin + b);
   }
-  const int64_t base = s.h_ptr[0];
-  for (auto& v : s.h_ptr) v -= base;
-  for (int r = 0; r < s.rows; r++)
-    if (s.h_ptr[r + 1] < s.h_ptr[r] || s.h_ptr[r + 1] - s.h_ptr[r] > other_dim)
-      return fail(EALS_ERR_ARG, "offsets not monotone / row longer than the other dimension at row %d", begin + r);
   s.nnz = s.h_ptr[s.rows];
   tm.lap("side: offsets to host+check");
 
@@ -385,20 +464,17 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
 
   tm.lap("side: alloc + copy indices");
   // indices must ascend strictly inside a row and stay in range (main.cpp:198-205 order)
+  int* sorted_flag = nullptr;
   if (s.rows > 0) {
     int* bad;
     OK(dev_alloc(&bad, 1));
     CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
     check_sorted_kernel<<<std::min((s.rows + 7) / 8, 64 * m->sm_count), 256, 0, m->stream>>>(s.ptr, s.idx, s.rows, other_dim, bad);
     OK(check_launch(m));
-    int h_bad = 0;
-    CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    CU(cudaStreamSynchronize(m->stream));
-    cudaFree(bad);
-    if (h_bad) return fail(EALS_ERR_ARG, "indices inside a row must be strictly ascending and in range");
+    sorted_flag = bad;   // read back after the host-side bucketing below (overlaps the upload)
   }
 
-  tm.lap("side: validate sorted");
+  tm.lap("side: validate sorted (enqueued)");
   // counting sort of the rows into length buckets
   std::vector<int32_t> order((size_t)std::max(s.rows, 1));
   int count[kNumBuckets] = {0};
@@ -409,17 +485,38 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     lut[n] = (uint8_t)b;
   }
   std::vector<uint8_t> bucket((size_t)std::max(s.rows, 1));
-  for (int r = 0; r < s.rows; r++) {
-    const int64_t n = s.h_ptr[r + 1] - s.h_ptr[r];
-    const uint8_t b = lut[std::min<int64_t>(n, kLut - 1)];
-    bucket[r] = b;
-    count[b]++;
+  {
+    // stable counting sort, chunked over host threads: per-chunk histograms, then per-chunk bases
+    int T = 1;
+    int cnt_t[kMaxHostThreads][kNumBuckets];
+    for (auto& c : cnt_t) for (int& v : c) v = 0;
+    const int64_t* hp = s.h_ptr.data();
+    parallel_chunks(s.rows, &T, [&](int t, int64_t b0, int64_t b1) {
+      int local[kNumBuckets] = {0};
+      for (int64_t r = b0; r < b1; r++) {
+        const int64_t n = hp[r + 1] - hp[r];
+        const uint8_t b = lut[std::min<int64_t>(n, kLut - 1)];
+        bucket[r] = b;
+        local[b]++;
+      }
+      for (int b = 0; b < kNumBuckets; b++) cnt_t[t][b] = local[b];
+    });
+    for (int b = 0; b < kNumBuckets; b++)
+      for (int t = 0; t < T; t++) count[b] += cnt_t[t][b];
+    s.first[0] = 0;
+    for (int b = 0; b < kNumBuckets; b++) s.first[b + 1] = s.first[b] + count[b];
+    int base_t[kMaxHostThreads][kNumBuckets];
+    for (int b = 0; b < kNumBuckets; b++) {
+      int at = s.first[b];
+      for (int t = 0; t < T; t++) { base_t[t][b] = at; at += cnt_t[t][b]; }
+    }
+    int T2 = 1;
+    parallel_chunks(s.rows, &T2, [&](int t, int64_t b0, int64_t b1) {
+      int fill[kNumBuckets];
+      for (int b = 0; b < kNumBuckets; b++) fill[b] = base_t[t][b];
+      for (int64_t r = b0; r < b1; r++) order[fill[bucket[r]]++] = (int32_t)r;
+    });
   }
-  s.first[0] = 0;
-  for (int b = 0; b < kNumBuckets; b++) s.first[b + 1] = s.first[b] + count[b];
-  int fill[kNumBuckets];
-  for (int b = 0; b < kNumBuckets; b++) fill[b] = s.first[b];
-  for (int r = 0; r < s.rows; r++) order[fill[bucket[r]]++] = r;
   // long rows: longest first, so the tail of the launch is made of the cheapest rows
   std::stable_sort(order.begin() + s.first[kHeavyBucket], order.begin() + s.first[kHeavyBucket + 1],
                    [&](int a, int b) {
@@ -428,14 +525,22 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
   OK(dev_reserve(&s.order, &s.cap_order, order.size()));
   CU(cudaMemcpyAsync(s.order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, m->stream));
 
-  tm.lap("side: bucket rows");
+  if (sorted_flag) {
+    int h_bad = 0;
+    CU(cudaMemcpyAsync(&h_bad, sorted_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    cudaFree(sorted_flag);
+    if (h_bad) return fail(EALS_ERR_ARG, "indices inside a row must be strictly ascending and in range");
+  }
+  tm.lap("side: bucket rows + validate");
   // heavy rows -> slabs ("units") of kSlab nonzeros and batches of rows
   {
     const int hb = s.first[kHeavyBucket], he = s.first[kHeavyBucket + 1];
     s.n_hrows = he - hb;
-    std::vector<int32_t> unit_row, unit_hrow, unit_cnt, hrow_id;
+    std::vector<int32_t> unit_row, unit_hrow, unit_cnt, hrow_id, grp_unit0, grp_cnt;
     std::vector<int64_t> unit_off, unit_poff;
     s.h_hrow_unit0.clear(); s.h_hrow_units.clear(); s.batches.clear(); s.h_row_to_hrow.clear();
+    s.h_hrow_grp0.clear(); s.h_hrow_grps.clear();
     {
       int64_t hn = 0;
       for (int h = 0; h < s.n_hrows; h++) { const int r = order[hb + h]; hn += s.h_ptr[r + 1] - s.h_ptr[r]; }
@@ -470,6 +575,12 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
         unit_cnt.push_back((int)std::min<int64_t>(eals::kSlab, n - o));
       }
       s.h_hrow_units.push_back(units);
+      s.h_hrow_grp0.push_back((int)grp_unit0.size());
+      s.h_hrow_grps.push_back((units + 31) / 32);
+      for (int q = 0; q < units; q += 32) {
+        grp_unit0.push_back(s.h_hrow_unit0.back() + q);
+        grp_cnt.push_back(std::min(32, units - q));
+      }
       poff += n;
     }
     if (s.n_hrows) {
@@ -495,11 +606,20 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     OK(up64(&s.unit_off, &s.cap_unit_off, unit_off)); OK(up64(&s.unit_poff, &s.cap_unit_poff, unit_poff));
     OK(up32(&s.hrow_id, &s.cap_hrow_id, hrow_id)); OK(up32(&s.hrow_unit0, &s.cap_hrow_unit0, s.h_hrow_unit0));
     OK(up32(&s.hrow_units, &s.cap_hrow_units, s.h_hrow_units));
+    OK(up32(&s.hrow_grp0, &s.cap_hrow_grp0, s.h_hrow_grp0)); OK(up32(&s.hrow_grps, &s.cap_hrow_grps, s.h_hrow_grps));
+    OK(up32(&s.grp_unit0, &s.cap_grp_unit0, grp_unit0)); OK(up32(&s.grp_cnt, &s.cap_grp_cnt, grp_cnt));
+    s.n_groups = (int)grp_unit0.size();
+    OK(build_launch_order(m, s));
     OK(dev_reserve(&s.pred, &s.cap_pred, (size_t)s.heavy_nnz));
     OK(dev_reserve(&s.delta, &s.cap_delta, (size_t)s.n_hrows * 16));
     CU(cudaStreamSynchronize(m->stream));   // the host vectors above go out of scope
     // size the partials scratch now: a reallocation in the middle of a sweep would synchronise
-    OK(ensure_partials(m, (size_t)(s.max_batch_units + (s.max_batch_units + 31) / 32 + 2) * eals::kPartLen));
+    {
+      int max_groups = 0;
+      for (const auto& b : s.batches)
+        max_groups = std::max(max_groups, s.h_hrow_grp0[b.h1 - 1] + s.h_hrow_grps[b.h1 - 1] - s.h_hrow_grp0[b.h0]);
+      OK(ensure_partials(m, (size_t)(s.max_batch_units + max_groups + 2) * eals::kPartLen));
+    }
   }
   tm.lap("side: heavy units + upload");
   CU(cudaStreamSynchronize(m->stream));
@@ -607,14 +727,13 @@ int launch_cd_warp_block(eals_model* m, const CdSide& a, const int32_t* order, i
   using Sm = eals::WarpBlockSmem<LD, MAXM>;
   // persistent CTAs, one per SM: S cache + as many row-warps as fit the 227 KB of shared memory
   const size_t budget = 227 * 1024 - Sm::kS;
-  int wpb = (int)std::min<size_t>(12, std::max<size_t>(1, budget / Sm::kBytesPerWarp));
+  int wpb = (int)std::min<size_t>(Sm::kMaxWarps, std::max<size_t>(1, budget / Sm::kBytesPerWarp));
   static int env_wpb = getenv("EALS_WARP_WPB") ? atoi(getenv("EALS_WARP_WPB")) : 0;
   if (env_wpb > 0) wpb = std::min(env_wpb, wpb);
   const size_t smem = Sm::kS + Sm::kBytesPerWarp * wpb;
   auto kern = eals::cd_warp_block_kernel<LD, MAXM, USER>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int ctas_per_sm = std::max<int>(1, (int)((227 * 1024) / smem));
-  const int grid = std::min((count + wpb - 1) / wpb, m->sm_count * std::min(ctas_per_sm, 4));
+  const int grid = std::min((count + wpb - 1) / wpb, m->sm_count);
   kern<<<grid, wpb * 32, smem, m->stream>>>(a, order, first, count);
   return check_launch(m);
 }
@@ -629,24 +748,38 @@ int launch_cd_row_block(eals_model* m, const CdSide& a, const int32_t* order, in
   return check_launch(m);
 }
 
+template <int LD, int TW, bool USER>
+int launch_cd_team(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
+  if (count <= 0) return EALS_OK;
+  using Sm = eals::TeamSmem<LD, TW>;
+  auto kern = eals::cd_team_kernel<LD, TW, USER>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::kBytes));
+  kern<<<count, TW * 32, Sm::kBytes, m->stream>>>(a, order, first);
+  return check_launch(m);
+}
+
 eals::HeavyUnits heavy_units(const Side& s) {
   eals::HeavyUnits hu;
   hu.unit_row = s.unit_row; hu.unit_hrow = s.unit_hrow; hu.unit_off = s.unit_off; hu.unit_poff = s.unit_poff;
   hu.unit_cnt = s.unit_cnt; hu.hrow_id = s.hrow_id; hu.hrow_unit0 = s.hrow_unit0; hu.hrow_units = s.hrow_units;
+  hu.hrow_grp0 = s.hrow_grp0; hu.hrow_grps = s.hrow_grps; hu.grp_unit0 = s.grp_unit0; hu.grp_cnt = s.grp_cnt;
+  hu.launch = nullptr;
   return hu;
 }
 
 // One batch of heavy rows: prediction cache, then per factor block a partials launch (which also
 // applies the previous block's cache update) and a solve launch.
 template <int LD, bool USER>
-int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b) {
+int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b, bool canonical) {
   const int nu = b.u1 - b.u0, nh = b.h1 - b.h0;
   if (nu <= 0) return EALS_OK;
-  const eals::HeavyUnits hu = heavy_units(s);
+  eals::HeavyUnits hu = heavy_units(s);
+  static const bool no_order = getenv("EALS_HEAVY_ORDER") && getenv("EALS_HEAVY_ORDER")[0] == '0';
+  if (canonical && !no_order) hu.launch = s.unit_launch + b.u0;   // neighbour order (one of s.batches)
   const int nblocks = (m->K + eals::kFB - 1) / eals::kFB;
-  // level-2 partials (one per group of 32 units) live behind the unit partials
-  const int ngroups = (nu + 31) / 32;
-  const bool two_level = nh == 1 && nu > 512;
+  // group sums (one per <= 32 consecutive units of a row) live behind the unit partials
+  const int g0 = s.h_hrow_grp0[b.h0];
+  const int ngroups = s.h_hrow_grp0[b.h1 - 1] + s.h_hrow_grps[b.h1 - 1] - g0;
   OK(ensure_partials(m, (size_t)(nu + ngroups) * eals::kPartLen));
   double* part = m->partials;
   double* part2 = m->partials + (size_t)nu * eals::kPartLen;
@@ -657,21 +790,13 @@ int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b
     OK(check_launch(m));
   }
   for (int fb = 0; fb <= nblocks; fb++) {
-    if (fb == nblocks) {   // last cache update; only needed when the symmetric cache keeps the result
-      if (!a.pc_out.n) break;
-      step<<<nu, eals::kBlkThreads, eals::HeavySmem::kBytes, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
-      OK(check_launch(m));
-      break;
-    }
+    if (fb == nblocks && !a.pc_out.n) break;   // last cache update: only when the symmetric cache keeps the result
     step<<<nu, eals::kBlkThreads, eals::HeavySmem::kBytes, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
     OK(check_launch(m));
-    if (two_level) {
-      eals::heavy_reduce_kernel<<<ngroups, eals::kBlkThreads, 0, m->stream>>>(part, nu, part2);
-      OK(check_launch(m));
-      eals::heavy_solve_kernel<LD, USER><<<nh, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.h0, b.u0, fb, part2, ngroups, s.delta);
-    } else {
-      eals::heavy_solve_kernel<LD, USER><<<nh, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.h0, b.u0, fb, part, 0, s.delta);
-    }
+    if (fb == nblocks) break;
+    eals::heavy_reduce_kernel<<<ngroups, eals::kBlkThreads, 0, m->stream>>>(part, hu, g0, b.u0, part2);
+    OK(check_launch(m));
+    eals::heavy_solve_kernel<LD, USER><<<nh, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.h0, g0, fb, part2, s.delta);
     OK(check_launch(m));
   }
   return EALS_OK;
@@ -684,41 +809,37 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     if (n == 0) return EALS_OK;
     if (n > kBucketMax[kHeavyBucket - 1]) {
       const int h = s.h_row_to_hrow[only_row];
-      return run_heavy_batch<LD, USER>(m, s, a, HeavyBatch{h, h + 1, s.h_hrow_unit0[h], s.h_hrow_unit0[h] + s.h_hrow_units[h]});
+      return run_heavy_batch<LD, USER>(m, s, a, HeavyBatch{h, h + 1, s.h_hrow_unit0[h], s.h_hrow_unit0[h] + s.h_hrow_units[h]}, false);
     }
     OK(ensure_partials(m, 16));
     int32_t* one = reinterpret_cast<int32_t*>(m->partials);
     CU(cudaMemcpyAsync(one, &only_row, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
     if (n <= 32) return launch_cd_warp_block<LD, 1, USER>(m, a, one, 0, 1);
-    if (n <= 64) return launch_cd_row_block<LD, 2, 1, USER>(m, a, one, 0, 1);
-    if (n <= 128) return launch_cd_row_block<LD, 4, 1, USER>(m, a, one, 0, 1);
-    if (n <= 256) return launch_cd_row_block<LD, 8, 1, USER>(m, a, one, 0, 1);
+    if (n <= 64) return launch_cd_warp_block<LD, 2, USER>(m, a, one, 0, 1);
+    if (n <= 128) return launch_cd_warp_block<LD, 4, USER>(m, a, one, 0, 1);
+    if (n <= 256) return launch_cd_team<LD, 8, USER>(m, a, one, 0, 1);
     return launch_cd_row_block<LD, 8, 2, USER>(m, a, one, 0, 1);
   }
   // heavy rows first: their launch chain is the longest
   const int t0 = USER ? T_U_HEAVY : T_I_HEAVY;
   tic(m, t0);
-  for (const HeavyBatch& b : s.batches) OK((run_heavy_batch<LD, USER>(m, s, a, b)));
+  for (const HeavyBatch& b : s.batches) OK((run_heavy_batch<LD, USER>(m, s, a, b, true)));
   toc(m, t0);
   tic(m, t0 + 1);
-  OK((launch_cd_row_block<LD, 8, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));
-  OK((launch_cd_row_block<LD, 8, 1, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
+  OK((launch_cd_row_block<LD, 8, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));   // 257..512
+  OK((launch_cd_team<LD, 8, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));           // 129..256
   toc(m, t0 + 1);
   tic(m, t0 + 2);
+  // EALS_WARP_SEQ=1: the plain sequential form (one reduction + one divide per factor) for A/B runs;
+  // measured on c4 it is 2.6x slower than the blocked form (profiles/README.md r01h)
   static const bool seq = getenv("EALS_WARP_SEQ") && getenv("EALS_WARP_SEQ")[0] == '1';
-  if (seq) {   // the plain sequential form (one reduction + one divide per factor), kept for comparison
+  if (seq) {
     OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
     OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
     OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
-  } else {
-    static const bool warp_only = getenv("EALS_WARP_ONLY") && getenv("EALS_WARP_ONLY")[0] == '1';
-    if (warp_only) {   // rows of 33..128 nonzeros as one warp each (comparison)
-      OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
-      OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
-    } else {           // ... or as teams of 4 / 2 warps
-      OK((launch_cd_row_block<LD, 4, 1, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
-      OK((launch_cd_row_block<LD, 2, 1, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
-    }
+  } else {   // one warp per row up to 128 nonzeros: no CTA barrier anywhere in the row loop
+    OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+    OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
     OK((launch_cd_warp_block<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
   }
   toc(m, t0 + 2);
