@@ -140,6 +140,10 @@ struct Side {
   int32_t *hrow_id = nullptr, *hrow_unit0 = nullptr, *hrow_units = nullptr;
   int32_t *hrow_grp0 = nullptr, *hrow_grps = nullptr, *grp_unit0 = nullptr, *grp_cnt = nullptr;
   int32_t* unit_launch = nullptr;     // launch order of the canonical batches (see HeavyUnits::launch)
+  uint32_t *sort_keys = nullptr, *sort_keys_out = nullptr;   // scratch of build_launch_order, kept across setTrain
+  int32_t* sort_vals = nullptr;
+  unsigned char* sort_tmp = nullptr;
+  size_t cap_sort_keys = 0, cap_sort_keys_out = 0, cap_sort_vals = 0, cap_sort_tmp = 0;
   int n_groups = 0;
   std::vector<int32_t> h_hrow_grp0, h_hrow_grps;
   std::vector<int32_t> h_hrow_unit0, h_hrow_units;
@@ -181,6 +185,7 @@ struct eals_model {
   double acc_ms[T_COUNT] = {0};
   int64_t acc_calls[T_COUNT] = {0};
   bool factors_set = false;
+  int* flags = nullptr;          // [8] device scratch for validation kernels (no malloc/free per call)
   eals::PeerSet peersU = {}, peersV = {};   // IPC mappings of the other ranks' U / V replicas
   // symmetric prediction cache (single-rank models only)
   double* pc_u = nullptr;        // predictions of the owned user rows' nonzeros (CSR order)
@@ -222,6 +227,7 @@ void free_side(Side& s) {
   cudaFree(s.unit_row); cudaFree(s.unit_hrow); cudaFree(s.unit_cnt); cudaFree(s.unit_off); cudaFree(s.unit_poff);
   cudaFree(s.hrow_id); cudaFree(s.hrow_unit0); cudaFree(s.hrow_units);
   cudaFree(s.hrow_grp0); cudaFree(s.hrow_grps); cudaFree(s.grp_unit0); cudaFree(s.grp_cnt); cudaFree(s.unit_launch);
+  cudaFree(s.sort_keys); cudaFree(s.sort_keys_out); cudaFree(s.sort_vals); cudaFree(s.sort_tmp);
   s = Side();
 }
 
@@ -345,8 +351,7 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   OK(dev_reserve(&m->pc_i, &m->cap_pc_i, (size_t)ni));
   OK(dev_reserve(&m->map_u, &m->cap_map_u, (size_t)nu));
   OK(dev_reserve(&m->map_i, &m->cap_map_i, (size_t)ni));
-  int* bad;
-  OK(dev_alloc(&bad, 1));
+  int* bad = m->flags + 2;
   CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
   CU(cudaMemsetAsync(m->map_u, 0xff, sizeof(uint32_t) * (size_t)nu, m->stream));   // unreached CSR entries stay invalid
   {
@@ -360,7 +365,7 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   int h_bad = 0;
   CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
-  cudaFree(bad); cudaFree(t_rp); cudaFree(t_cp); cudaFree(t_ci); cudaFree(t_ri);
+  if (t_rp) { cudaFree(t_rp); cudaFree(t_cp); cudaFree(t_ci); cudaFree(t_ri); }
   if (h_bad) return fail(EALS_ERR_ARG, "the CSR and CSC arrays do not describe the same matrix");
   // destination tables; the own rank's entries are filled now, the peers' by eals_ipc_attach
   const int nr = single ? 1 : m->n_ranks, me = single ? 0 : m->rank;
@@ -391,17 +396,16 @@ __global__ void unit_key_kernel(const int32_t* __restrict__ idx, const int64_t* 
 int build_launch_order(eals_model* m, Side& s) {
   OK(dev_reserve(&s.unit_launch, &s.cap_unit_launch, (size_t)std::max(s.n_units, 1)));
   if (s.n_units == 0) return EALS_OK;
-  uint32_t *keys = nullptr, *keys_out = nullptr;
-  int32_t* vals = nullptr;
-  void* tmp = nullptr;
-  int rc = EALS_OK;
-  auto done = [&](int code) { cudaFree(keys); cudaFree(keys_out); cudaFree(vals); cudaFree(tmp); return code; };
-  if ((rc = dev_alloc(&keys, (size_t)s.max_batch_units)) != EALS_OK) return done(rc);
-  if ((rc = dev_alloc(&keys_out, (size_t)s.max_batch_units)) != EALS_OK) return done(rc);
-  if ((rc = dev_alloc(&vals, (size_t)s.max_batch_units)) != EALS_OK) return done(rc);
+  OK(dev_reserve(&s.sort_keys, &s.cap_sort_keys, (size_t)s.max_batch_units));
+  OK(dev_reserve(&s.sort_keys_out, &s.cap_sort_keys_out, (size_t)s.max_batch_units));
+  OK(dev_reserve(&s.sort_vals, &s.cap_sort_vals, (size_t)s.max_batch_units));
+  uint32_t *keys = s.sort_keys, *keys_out = s.sort_keys_out;
+  int32_t* vals = s.sort_vals;
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, s.unit_launch, s.max_batch_units, 0, 32, m->stream);
-  if (cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)) != cudaSuccess) return done(fail(EALS_ERR_ALLOC, "scratch for the slab sort"));
+  OK(dev_reserve(&s.sort_tmp, &s.cap_sort_tmp, std::max<size_t>(tmp_bytes, 16)));
+  void* tmp = s.sort_tmp;
+  auto done = [&](int code) { return code; };
   for (const HeavyBatch& b : s.batches) {
     const int n = b.u1 - b.u0;
     unit_key_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(s.idx, s.unit_off, b.u0, n, keys, vals);
@@ -466,8 +470,7 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
   // indices must ascend strictly inside a row and stay in range (main.cpp:198-205 order)
   int* sorted_flag = nullptr;
   if (s.rows > 0) {
-    int* bad;
-    OK(dev_alloc(&bad, 1));
+    int* bad = m->flags + (&s == &m->users ? 0 : 1);
     CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
     check_sorted_kernel<<<std::min((s.rows + 7) / 8, 64 * m->sm_count), 256, 0, m->stream>>>(s.ptr, s.idx, s.rows, other_dim, bad);
     OK(check_launch(m));
@@ -484,6 +487,10 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     while (n > kBucketMax[b]) b++;
     lut[n] = (uint8_t)b;
   }
+  // EALS_HEAVY_MIN: rows longer than this go to the slab pipeline (default: the last team bucket's limit)
+  const int heavy_min = getenv("EALS_HEAVY_MIN") ? std::max(32, atoi(getenv("EALS_HEAVY_MIN"))) : kBucketMax[kHeavyBucket - 1];
+  for (int n = 0; n < kLut; n++)
+    if (n > heavy_min) lut[n] = (uint8_t)kHeavyBucket;
   std::vector<uint8_t> bucket((size_t)std::max(s.rows, 1));
   {
     // stable counting sort, chunked over host threads: per-chunk histograms, then per-chunk bases
@@ -529,7 +536,6 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     int h_bad = 0;
     CU(cudaMemcpyAsync(&h_bad, sorted_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
-    cudaFree(sorted_flag);
     if (h_bad) return fail(EALS_ERR_ARG, "indices inside a row must be strictly ascending and in range");
   }
   tm.lap("side: bucket rows + validate");
@@ -774,7 +780,7 @@ int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b
   const int nu = b.u1 - b.u0, nh = b.h1 - b.h0;
   if (nu <= 0) return EALS_OK;
   eals::HeavyUnits hu = heavy_units(s);
-  static const bool no_order = getenv("EALS_HEAVY_ORDER") && getenv("EALS_HEAVY_ORDER")[0] == '0';
+  const bool no_order = getenv("EALS_HEAVY_ORDER") && getenv("EALS_HEAVY_ORDER")[0] == '0';   // A/B runs and tests
   if (canonical && !no_order) hu.launch = s.unit_launch + b.u0;   // neighbour order (one of s.batches)
   const int nblocks = (m->K + eals::kFB - 1) / eals::kFB;
   // group sums (one per <= 32 consecutive units of a row) live behind the unit partials
@@ -807,7 +813,7 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   if (only_row >= 0) {  // single-row API: a one-entry order list in scratch
     const int64_t n = s.h_ptr[only_row + 1] - s.h_ptr[only_row];
     if (n == 0) return EALS_OK;
-    if (n > kBucketMax[kHeavyBucket - 1]) {
+    if (!s.h_row_to_hrow.empty() && s.h_row_to_hrow[only_row] >= 0) {
       const int h = s.h_row_to_hrow[only_row];
       return run_heavy_batch<LD, USER>(m, s, a, HeavyBatch{h, h + 1, s.h_hrow_unit0[h], s.h_hrow_unit0[h] + s.h_hrow_units[h]}, false);
     }
@@ -1226,7 +1232,7 @@ int eals_destroy(eals_model* m) {
   free_side(m->users);
   free_side(m->items);
   cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
-  cudaFree(m->terms); cudaFree(m->partials);
+  cudaFree(m->terms); cudaFree(m->partials); cudaFree(m->flags);
   cudaFree(m->pc_u); cudaFree(m->pc_i); cudaFree(m->map_u); cudaFree(m->map_i);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
@@ -1291,6 +1297,7 @@ int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t
   TRY(dev_alloc(&m->SV, (size_t)m->LD * m->LD));
   TRY(dev_alloc(&m->Wi, (size_t)m->N));
   TRY(dev_alloc(&m->terms, 4));
+  TRY(dev_alloc(&m->flags, 8));
   TRYCU(cudaMemsetAsync(m->U, 0, sizeof(double) * (size_t)m->M * m->LD, m->stream));
   TRYCU(cudaMemsetAsync(m->V, 0, sizeof(double) * (size_t)m->N * m->LD, m->stream));
   TRYCU(cudaMemsetAsync(m->SU, 0, sizeof(double) * (size_t)m->LD * m->LD, m->stream));

@@ -214,6 +214,44 @@ def test_ultra_heavy_row_two_level_reduction():
     assert abs(lg - lc) <= 1e-10 * abs(lc)
 
 
+def test_slab_launch_order_does_not_change_a_single_bit(monkeypatch):
+    """The heavy slabs are launched in neighbour order for L2 reuse; partial sums are stored and added
+    by canonical slot, so the result must be bit-identical to the canonical launch order."""
+    M, N, K = 5000, 40, 32
+    row_ptr, col_idx = _heavy_matrix(M, N, heavy_cols=[1, 9, 17, 30], heavy_len=2500, seed=5)
+    out = []
+    for order in ("1", "0"):
+        monkeypatch.setenv("EALS_HEAVY_ORDER", order)
+        fals, _ = _models(M, N, row_ptr, col_idx, K)
+        for _ in range(2):
+            fals.update_user(); fals.update_item()
+        out.append((fals.U, fals.V))
+        fals.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_rows_of_every_bucket_boundary_length():
+    """Row lengths on both sides of every kernel-family boundary (32/33, 64/65, 128/129, 256/257,
+    512/513) in one matrix, K not a multiple of 16."""
+    lens = [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 700]
+    M, N, K = len(lens) * 3, 1200, 40
+    rng = np.random.default_rng(21)
+    row_ptr, cols = [0], []
+    for u in range(M):
+        n = lens[u % len(lens)]
+        cols.append(np.sort(rng.choice(N, size=n, replace=False)).astype(np.int32))
+        row_ptr.append(row_ptr[-1] + n)
+    row_ptr, col_idx = np.asarray(row_ptr, np.int64), np.concatenate(cols)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        assert np.abs(fals.U - port.U).max() < 1e-10
+        fals.update_item(); port.update_item()
+        assert np.abs(fals.V - port.V).max() < 1e-10
+    lg, lc = fals.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc)
+
+
 def test_single_row_api_and_patches():
     M, N, K = 150, 120, 16
     row_ptr, col_idx = random_csr(M, N, 9, seed=9)
