@@ -43,7 +43,7 @@ namespace eals {
 constexpr int kBlkThreads = 256;
 constexpr int kBlkWarps = kBlkThreads / 32;
 constexpr int kPartLen = 208;   // 3 tiles x 32 lanes x 2 (C fragments) + 16 (P)
-constexpr int kSlab = 256;      // nonzeros per slab of a heavy row (one per thread)
+constexpr int kMaxSlab = 256;   // nonzeros per slab of a heavy row (one per thread): 128 or 256, chosen by the host
 
 // ---- swizzled tile: row r = 128 bytes, 16-byte chunk c stored at chunk position c ^ (r & 7) ----
 __device__ __forceinline__ uint32_t tile_chunk_off(int r, int c) { return (uint32_t)(r * 128 + (((c ^ r) & 7) << 4)); }
@@ -878,43 +878,56 @@ cd_team_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
 // launch pair per factor block over a BATCH of rows small enough that the block's lines stay in L2
 // between the partials launch and the deferred cache update of the next one.
 // ---------------------------------------------------------------------------------------------
+// One slab ("unit") of a heavy row, 32 bytes: read with two 16-byte loads at the top of the kernel.
+struct __align__(16) UnitDesc {
+  int64_t off;      // offset of the unit's first nonzero in the side's idx/val arrays
+  int64_t poff;     // offset of the same nonzero in the compact prediction cache
+  int32_t cnt;      // nonzeros in the unit (<= slab size)
+  int32_t row;      // owned-row id
+  int32_t hrow;     // index of that row among the heavy rows (delta / x slots)
+  int32_t slot;     // canonical unit id = slot of its partial sums
+};
+
 struct HeavyUnits {
-  const int32_t* unit_row;     // owned-row id of the unit
-  const int32_t* unit_hrow;    // index of that row among the heavy rows (delta / x slots)
-  const int64_t* unit_off;     // offset of the unit's first nonzero in the side's idx/val arrays
-  const int64_t* unit_poff;    // offset of the same nonzero in the compact prediction cache
-  const int32_t* unit_cnt;     // nonzeros in the unit (<= kSlab)
+  // Descriptors of the units a launch covers, in LAUNCH order (CTA b takes units[b]).  Canonical
+  // order is row by row; the launch order of a whole batch sorts the slabs by the id of their FIRST
+  // neighbour, so that CTAs running at the same time gather (largely) the same neighbour rows: with
+  // every heavy row of a side in one batch, a neighbour's line is fetched from HBM once per step
+  // and served to the other slabs — and to the deferred cache update of the next step — from L2
+  // (before: 243 B of DRAM reads per nonzero and block, L2 hit rate 9 %; profiles/README.md r01f/h).
+  const UnitDesc* units;
   const int32_t* hrow_id;      // owned-row id of heavy row h
-  const int32_t* hrow_unit0;   // first unit of heavy row h
-  const int32_t* hrow_units;   // number of units of heavy row h
   const int32_t* hrow_grp0;    // first reduction group of heavy row h (groups of <= 32 consecutive units)
   const int32_t* hrow_grps;    // number of groups of heavy row h
-  const int32_t* grp_unit0;    // first unit of group g
+  const int32_t* grp_unit0;    // first unit (canonical id) of group g
   const int32_t* grp_cnt;      // units in group g
-  // Launch order of a batch's units (nullptr: canonical order).  Canonical order is row by row; the
-  // launch order sorts the slabs by the id of their FIRST neighbour, so that CTAs running at the same
-  // time gather (largely) the same neighbour rows: with every heavy row of a side in one batch, a
-  // neighbour's line is then fetched from HBM once per step and served to the other slabs from L2,
-  // instead of once per slab and again for the deferred cache update (measured before: 243 B of
-  // DRAM reads per nonzero and block, L2 hit rate 9 %; profiles/README.md r01f).
-  const int32_t* launch;
 };
+
+__device__ __forceinline__ UnitDesc load_unit(const UnitDesc* p) {
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  UnitDesc d;
+  d.off = ((int64_t)(uint32_t)a.y << 32) | (uint32_t)a.x;
+  d.poff = ((int64_t)(uint32_t)a.w << 32) | (uint32_t)a.z;
+  d.cnt = b.x; d.row = b.y; d.hrow = b.z; d.slot = b.w;
+  return d;
+}
 
 // p_j = <x_row, y_j> for every nonzero of the units [u0, u0 + gridDim.x): 8 lanes per nonzero.
 template <int LD>
 __global__ void __launch_bounds__(kBlkThreads)
-heavy_pred_kernel(CdSide a, HeavyUnits hu, int u0, double* __restrict__ pred) {
+heavy_pred_kernel(CdSide a, HeavyUnits hu, double* __restrict__ pred) {
   __shared__ double x_s[LD];
   const int tid = threadIdx.x;
-  const int u = hu.launch ? hu.launch[blockIdx.x] : u0 + blockIdx.x;
-  const int row = hu.unit_row[u];
+  const UnitDesc ud = load_unit(hu.units + blockIdx.x);
+  const int row = ud.row;
   const double* xrow = a.X + (size_t)(a.row_base + row) * LD;
   for (int k = tid; k < LD; k += kBlkThreads) x_s[k] = xrow[k];
   __syncthreads();
-  const int64_t off = hu.unit_off[u], poff = hu.unit_poff[u];
-  const int cnt = hu.unit_cnt[u];
+  const int64_t off = ud.off, poff = ud.poff;
+  const int cnt = ud.cnt;
   const int g8 = tid >> 3, gl = tid & 7;
-  for (int j0 = 0; j0 < cnt; j0 += kBlkThreads / 8) {
+  for (int j0 = 0; j0 < cnt; j0 += kBlkThreads / 8) {   // cnt <= kMaxSlab
     const int j = j0 + g8;
     double acc = 0.0;
     if (j < cnt) {
@@ -933,40 +946,42 @@ heavy_pred_kernel(CdSide a, HeavyUnits hu, int u0, double* __restrict__ pred) {
   }
 }
 
+template <int SLAB>
 struct HeavySmem {
-  static constexpr size_t kTile = (size_t)kSlab * 128;       // x2: previous block (cache update) + this block
-  static constexpr size_t kIdx = (size_t)kSlab * 8;          // row base pointers
-  static constexpr size_t kCZ = (size_t)kSlab * 16;
-  // the per-warp reduction slots (8 x 208 doubles) reuse the previous-block tile once it is consumed
+  static constexpr size_t kTile = (size_t)SLAB * 128;       // x2: previous block (cache update) + this block
+  static constexpr size_t kIdx = (size_t)SLAB * 8;          // row base pointers
+  static constexpr size_t kCZ = (size_t)SLAB * 16;
+  // the per-warp reduction slots (SLAB/32 x 208 doubles) reuse the previous-block tile once it is consumed
   static constexpr size_t kBytes = 2 * kTile + kIdx + kCZ + 16 * 8;
+  static_assert((size_t)(SLAB / 32) * kPartLen * 8 <= kTile, "slots must fit the spare tile");
 };
-static_assert((size_t)kBlkWarps * kPartLen * 8 <= HeavySmem::kTile, "slots must fit the spare tile");
 
 // Step fb of the batch: (1) if fb > 0, apply the cache update of block fb-1 (needs that block's
 // lines again); (2) if fb < nblocks, form the slab's partial Gram and right-hand side of block fb
-// (tensor cores) and write them to partials[unit - u0].  Both tiles are requested up front (two
-// cp.async groups in flight), so a slab pays one memory round trip per step, not two.
-template <int LD, bool USER>
-__global__ void __launch_bounds__(kBlkThreads, 3)
+// (tensor cores) and write them to partials[slot].  Both tiles are requested up front (two cp.async
+// groups in flight), so a slab pays one memory round trip per step, not two; the slab descriptor is
+// one 32-byte record in launch order, so the dependent chain is descriptor -> indices -> gather.
+// One nonzero per thread: SLAB threads per CTA (256: 3 CTAs/SM, 128: 6 CTAs/SM).
+template <int LD, bool USER, int SLAB>
+__global__ void __launch_bounds__(SLAB, SLAB == 256 ? 3 : 6)
 heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* __restrict__ pred,
                   const double* __restrict__ delta, double* __restrict__ partials) {
   extern __shared__ __align__(128) unsigned char smem[];
+  using Sm = HeavySmem<SLAB>;
   unsigned char* tile_prev = smem;
-  unsigned char* tile = smem + HeavySmem::kTile;
-  const double** rowp_s = reinterpret_cast<const double**>(smem + 2 * HeavySmem::kTile);
-  double* c_s = reinterpret_cast<double*>(smem + 2 * HeavySmem::kTile + HeavySmem::kIdx);
-  double* z_s = c_s + kSlab;
-  double* delta_s = z_s + kSlab;
+  unsigned char* tile = smem + Sm::kTile;
+  const double** rowp_s = reinterpret_cast<const double**>(smem + 2 * Sm::kTile);
+  double* c_s = reinterpret_cast<double*>(smem + 2 * Sm::kTile + Sm::kIdx);
+  double* z_s = c_s + SLAB;
+  double* delta_s = z_s + SLAB;
   double* slots = reinterpret_cast<double*>(tile_prev);   // free again after the cache update
-  static_assert(kSlab == kBlkThreads, "one nonzero per thread");
 
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-  const int u = hu.launch ? hu.launch[blockIdx.x] : u0 + blockIdx.x;
-  const int row = hu.unit_row[u];
-  const int64_t off = hu.unit_off[u], poff = hu.unit_poff[u];
-  const int n = hu.unit_cnt[u];
+  const UnitDesc ud = load_unit(hu.units + blockIdx.x);
+  const int64_t off = ud.off, poff = ud.poff;
+  const int n = ud.cnt;
   const int n_pad = (n + 3) & ~3;
-  const int grow = a.row_base + row;
+  const int grow = a.row_base + ud.row;
   const double wi_row = USER ? 0.0 : a.Wi[grow];
 
   double pr = 0.0, cw = 0.0, wr = 0.0;
@@ -979,15 +994,15 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
     pr = (fb == 0 && a.use_cache) ? a.pc_in[off + tid] : pred[poff + tid];
   }
   c_s[tid] = cw;
-  if (fb > 0 && tid < 16) delta_s[tid] = delta[(size_t)hu.unit_hrow[u] * 16 + tid];
+  if (fb > 0 && tid < 16) delta_s[tid] = delta[(size_t)ud.hrow * 16 + tid];
   __syncthreads();
 
   if (fb > 0) {
-    stage_tile_rows(tile_prev, rowp_s, n, n_pad, fb - 1, tid, kBlkThreads);
+    stage_tile_rows(tile_prev, rowp_s, n, n_pad, fb - 1, tid, SLAB);
     cp_async_commit();
   }
   if (fb < nblocks) {
-    stage_tile_rows(tile, rowp_s, n, n_pad, fb, tid, kBlkThreads);
+    stage_tile_rows(tile, rowp_s, n, n_pad, fb, tid, SLAB);
     cp_async_commit();
   }
   if (fb > 0) {
@@ -1029,11 +1044,11 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
     slot[200 + (lane >> 2)] = frag[8];
   }
   __syncthreads();
-  if (tid < kPartLen) {
+  for (int i = tid; i < kPartLen; i += SLAB) {
     double sum = 0.0;
 #pragma unroll
-    for (int w = 0; w < kBlkWarps; w++) sum += slots[w * kPartLen + tid];
-    partials[(size_t)(u - u0) * kPartLen + tid] = sum;
+    for (int w = 0; w < SLAB / 32; w++) sum += slots[w * kPartLen + i];
+    partials[(size_t)(ud.slot - u0) * kPartLen + i] = sum;
   }
 }
 

@@ -135,11 +135,12 @@ struct Side {
   // heavy rows (bucket 7): row h = order[first[7] + h], longest first
   int n_hrows = 0, n_units = 0, max_batch_units = 0;
   int64_t heavy_nnz = 0;
-  int32_t *unit_row = nullptr, *unit_hrow = nullptr, *unit_cnt = nullptr;
-  int64_t *unit_off = nullptr, *unit_poff = nullptr;
+  eals::UnitDesc* units_canon = nullptr;    // slab descriptors, canonical order (row by row)
+  eals::UnitDesc* units_launch = nullptr;   // the same, every canonical batch in neighbour order
+  int slab = eals::kMaxSlab;                // nonzeros per slab (= threads of a heavy_step CTA)
   int32_t *hrow_id = nullptr, *hrow_unit0 = nullptr, *hrow_units = nullptr;
   int32_t *hrow_grp0 = nullptr, *hrow_grps = nullptr, *grp_unit0 = nullptr, *grp_cnt = nullptr;
-  int32_t* unit_launch = nullptr;     // launch order of the canonical batches (see HeavyUnits::launch)
+  int32_t* unit_launch = nullptr;     // scratch: sorted canonical unit ids of a batch
   uint32_t *sort_keys = nullptr, *sort_keys_out = nullptr;   // scratch of build_launch_order, kept across setTrain
   int32_t* sort_vals = nullptr;
   unsigned char* sort_tmp = nullptr;
@@ -152,8 +153,7 @@ struct Side {
   double* pred = nullptr;             // prediction cache of the heavy rows (compact)
   double* delta = nullptr;            // [n_hrows][16] factor changes of the current block
   // capacities (elements) of the device arrays above, see dev_reserve
-  size_t cap_ptr = 0, cap_idx = 0, cap_val = 0, cap_order = 0, cap_unit_row = 0, cap_unit_hrow = 0, cap_unit_cnt = 0,
-         cap_unit_off = 0, cap_unit_poff = 0, cap_hrow_id = 0, cap_hrow_unit0 = 0, cap_hrow_units = 0, cap_pred = 0,
+  size_t cap_ptr = 0, cap_idx = 0, cap_val = 0, cap_order = 0, cap_units_canon = 0, cap_units_launch = 0, cap_hrow_id = 0, cap_hrow_unit0 = 0, cap_hrow_units = 0, cap_pred = 0,
          cap_delta = 0, cap_hrow_grp0 = 0, cap_hrow_grps = 0, cap_grp_unit0 = 0, cap_grp_cnt = 0, cap_unit_launch = 0;
   std::vector<int64_t> h_ptr;         // host copy of ptr (rebased to 0)
 };
@@ -224,7 +224,7 @@ int check_launch(eals_model* m) {
 void free_side(Side& s) {
   cudaFree(s.ptr); cudaFree(s.idx); cudaFree(s.val); cudaFree(s.order);
   cudaFree(s.pred); cudaFree(s.delta);
-  cudaFree(s.unit_row); cudaFree(s.unit_hrow); cudaFree(s.unit_cnt); cudaFree(s.unit_off); cudaFree(s.unit_poff);
+  cudaFree(s.units_canon); cudaFree(s.units_launch);
   cudaFree(s.hrow_id); cudaFree(s.hrow_unit0); cudaFree(s.hrow_units);
   cudaFree(s.hrow_grp0); cudaFree(s.hrow_grps); cudaFree(s.grp_unit0); cudaFree(s.grp_cnt); cudaFree(s.unit_launch);
   cudaFree(s.sort_keys); cudaFree(s.sort_keys_out); cudaFree(s.sort_vals); cudaFree(s.sort_tmp);
@@ -384,17 +384,24 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   return EALS_OK;
 }
 
-__global__ void unit_key_kernel(const int32_t* __restrict__ idx, const int64_t* __restrict__ unit_off, int u0, int n,
+__global__ void unit_key_kernel(const int32_t* __restrict__ idx, const eals::UnitDesc* __restrict__ canon, int u0, int n,
                                 uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  keys[t] = (uint32_t)idx[unit_off[u0 + t]];
+  keys[t] = (uint32_t)idx[canon[u0 + t].off];
   vals[t] = u0 + t;
+}
+
+__global__ void unit_gather_kernel(const eals::UnitDesc* __restrict__ canon, const int32_t* __restrict__ sorted_ids, int n,
+                                   eals::UnitDesc* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = canon[sorted_ids[t]];
 }
 
 // Launch order of every canonical batch: its slabs sorted by the id of their first neighbour.
 int build_launch_order(eals_model* m, Side& s) {
   OK(dev_reserve(&s.unit_launch, &s.cap_unit_launch, (size_t)std::max(s.n_units, 1)));
+  OK(dev_reserve(&s.units_launch, &s.cap_units_launch, (size_t)std::max(s.n_units, 1)));
   if (s.n_units == 0) return EALS_OK;
   OK(dev_reserve(&s.sort_keys, &s.cap_sort_keys, (size_t)s.max_batch_units));
   OK(dev_reserve(&s.sort_keys_out, &s.cap_sort_keys_out, (size_t)s.max_batch_units));
@@ -408,10 +415,12 @@ int build_launch_order(eals_model* m, Side& s) {
   auto done = [&](int code) { return code; };
   for (const HeavyBatch& b : s.batches) {
     const int n = b.u1 - b.u0;
-    unit_key_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(s.idx, s.unit_off, b.u0, n, keys, vals);
+    unit_key_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(s.idx, s.units_canon, b.u0, n, keys, vals);
     if (cudaGetLastError() != cudaSuccess) return done(fail(EALS_ERR_CUDA, "unit_key_kernel launch"));
     if (cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, s.unit_launch + b.u0, n, 0, 32, m->stream) != cudaSuccess)
       return done(fail(EALS_ERR_CUDA, "slab sort"));
+    unit_gather_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(s.units_canon, s.unit_launch + b.u0, n, s.units_launch + b.u0);
+    if (cudaGetLastError() != cudaSuccess) return done(fail(EALS_ERR_CUDA, "unit_gather_kernel launch"));
   }
   if (cudaStreamSynchronize(m->stream) != cudaSuccess) return done(fail(EALS_ERR_CUDA, "slab sort sync"));
   return done(EALS_OK);
@@ -543,15 +552,17 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
   {
     const int hb = s.first[kHeavyBucket], he = s.first[kHeavyBucket + 1];
     s.n_hrows = he - hb;
-    std::vector<int32_t> unit_row, unit_hrow, unit_cnt, hrow_id, grp_unit0, grp_cnt;
-    std::vector<int64_t> unit_off, unit_poff;
+    std::vector<int32_t> hrow_id, grp_unit0, grp_cnt;
+    std::vector<eals::UnitDesc> units;
+    // EALS_SLAB=128|256: nonzeros per slab = threads per heavy_step CTA
+    s.slab = (getenv("EALS_SLAB") && atoi(getenv("EALS_SLAB")) == 256) ? 256 : 128;
     s.h_hrow_unit0.clear(); s.h_hrow_units.clear(); s.batches.clear(); s.h_row_to_hrow.clear();
     s.h_hrow_grp0.clear(); s.h_hrow_grps.clear();
     {
       int64_t hn = 0;
       for (int h = 0; h < s.n_hrows; h++) { const int r = order[hb + h]; hn += s.h_ptr[r + 1] - s.h_ptr[r]; }
-      const size_t est = (size_t)(hn / eals::kSlab) + (size_t)s.n_hrows + 1;
-      unit_row.reserve(est); unit_hrow.reserve(est); unit_cnt.reserve(est); unit_off.reserve(est); unit_poff.reserve(est);
+      const size_t est = (size_t)(hn / s.slab) + (size_t)s.n_hrows + 1;
+      units.reserve(est);
       hrow_id.reserve((size_t)s.n_hrows); s.h_hrow_unit0.reserve((size_t)s.n_hrows); s.h_hrow_units.reserve((size_t)s.n_hrows);
     }
     int64_t poff = 0, batch_nnz = 0;
@@ -563,7 +574,7 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
       const int r = order[hb + h];
       const int64_t n = s.h_ptr[r + 1] - s.h_ptr[r];
       if (h > cur.h0 && batch_nnz + n > batch_limit) {
-        cur.h1 = h; cur.u1 = (int)unit_row.size();
+        cur.h1 = h; cur.u1 = (int)units.size();
         s.batches.push_back(cur);
         cur = HeavyBatch{h, h, cur.u1, cur.u1};
         batch_nnz = 0;
@@ -571,29 +582,28 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
       batch_nnz += n;
       s.h_row_to_hrow[r] = h;
       hrow_id.push_back(r);
-      s.h_hrow_unit0.push_back((int)unit_row.size());
-      int units = 0;
-      for (int64_t o = 0; o < n; o += eals::kSlab, units++) {
-        unit_row.push_back(r);
-        unit_hrow.push_back(h);
-        unit_off.push_back(s.h_ptr[r] + o);
-        unit_poff.push_back(poff + o);
-        unit_cnt.push_back((int)std::min<int64_t>(eals::kSlab, n - o));
+      s.h_hrow_unit0.push_back((int)units.size());
+      int nunits = 0;
+      for (int64_t o = 0; o < n; o += s.slab, nunits++) {
+        eals::UnitDesc d;
+        d.off = s.h_ptr[r] + o; d.poff = poff + o; d.cnt = (int)std::min<int64_t>(s.slab, n - o);
+        d.row = r; d.hrow = h; d.slot = (int)units.size();
+        units.push_back(d);
       }
-      s.h_hrow_units.push_back(units);
+      s.h_hrow_units.push_back(nunits);
       s.h_hrow_grp0.push_back((int)grp_unit0.size());
-      s.h_hrow_grps.push_back((units + 31) / 32);
-      for (int q = 0; q < units; q += 32) {
+      s.h_hrow_grps.push_back((nunits + 31) / 32);
+      for (int q = 0; q < nunits; q += 32) {
         grp_unit0.push_back(s.h_hrow_unit0.back() + q);
-        grp_cnt.push_back(std::min(32, units - q));
+        grp_cnt.push_back(std::min(32, nunits - q));
       }
       poff += n;
     }
     if (s.n_hrows) {
-      cur.h1 = s.n_hrows; cur.u1 = (int)unit_row.size();
+      cur.h1 = s.n_hrows; cur.u1 = (int)units.size();
       s.batches.push_back(cur);
     }
-    s.n_units = (int)unit_row.size();
+    s.n_units = (int)units.size();
     s.heavy_nnz = poff;
     s.max_batch_units = 0;
     for (const auto& b : s.batches) s.max_batch_units = std::max(s.max_batch_units, b.u1 - b.u0);
@@ -602,14 +612,9 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
       if (!v.empty()) CU(cudaMemcpyAsync(*d, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, m->stream));
       return EALS_OK;
     };
-    auto up64 = [&](int64_t** d, size_t* cap, const std::vector<int64_t>& v) -> int {
-      OK(dev_reserve(d, cap, v.size()));
-      if (!v.empty()) CU(cudaMemcpyAsync(*d, v.data(), sizeof(int64_t) * v.size(), cudaMemcpyHostToDevice, m->stream));
-      return EALS_OK;
-    };
-    OK(up32(&s.unit_row, &s.cap_unit_row, unit_row)); OK(up32(&s.unit_hrow, &s.cap_unit_hrow, unit_hrow));
-    OK(up32(&s.unit_cnt, &s.cap_unit_cnt, unit_cnt));
-    OK(up64(&s.unit_off, &s.cap_unit_off, unit_off)); OK(up64(&s.unit_poff, &s.cap_unit_poff, unit_poff));
+    OK(dev_reserve(&s.units_canon, &s.cap_units_canon, std::max<size_t>(units.size(), 1)));
+    if (!units.empty())
+      CU(cudaMemcpyAsync(s.units_canon, units.data(), sizeof(eals::UnitDesc) * units.size(), cudaMemcpyHostToDevice, m->stream));
     OK(up32(&s.hrow_id, &s.cap_hrow_id, hrow_id)); OK(up32(&s.hrow_unit0, &s.cap_hrow_unit0, s.h_hrow_unit0));
     OK(up32(&s.hrow_units, &s.cap_hrow_units, s.h_hrow_units));
     OK(up32(&s.hrow_grp0, &s.cap_hrow_grp0, s.h_hrow_grp0)); OK(up32(&s.hrow_grps, &s.cap_hrow_grps, s.h_hrow_grps));
@@ -766,10 +771,9 @@ int launch_cd_team(eals_model* m, const CdSide& a, const int32_t* order, int fir
 
 eals::HeavyUnits heavy_units(const Side& s) {
   eals::HeavyUnits hu;
-  hu.unit_row = s.unit_row; hu.unit_hrow = s.unit_hrow; hu.unit_off = s.unit_off; hu.unit_poff = s.unit_poff;
-  hu.unit_cnt = s.unit_cnt; hu.hrow_id = s.hrow_id; hu.hrow_unit0 = s.hrow_unit0; hu.hrow_units = s.hrow_units;
+  hu.units = nullptr;
+  hu.hrow_id = s.hrow_id;
   hu.hrow_grp0 = s.hrow_grp0; hu.hrow_grps = s.hrow_grps; hu.grp_unit0 = s.grp_unit0; hu.grp_cnt = s.grp_cnt;
-  hu.launch = nullptr;
   return hu;
 }
 
@@ -781,7 +785,7 @@ int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b
   if (nu <= 0) return EALS_OK;
   eals::HeavyUnits hu = heavy_units(s);
   const bool no_order = getenv("EALS_HEAVY_ORDER") && getenv("EALS_HEAVY_ORDER")[0] == '0';   // A/B runs and tests
-  if (canonical && !no_order) hu.launch = s.unit_launch + b.u0;   // neighbour order (one of s.batches)
+  hu.units = ((canonical && !no_order) ? s.units_launch : s.units_canon) + b.u0;   // neighbour order for whole batches
   const int nblocks = (m->K + eals::kFB - 1) / eals::kFB;
   // group sums (one per <= 32 consecutive units of a row) live behind the unit partials
   const int g0 = s.h_hrow_grp0[b.h0];
@@ -789,15 +793,16 @@ int run_heavy_batch(eals_model* m, Side& s, const CdSide& a, const HeavyBatch& b
   OK(ensure_partials(m, (size_t)(nu + ngroups) * eals::kPartLen));
   double* part = m->partials;
   double* part2 = m->partials + (size_t)nu * eals::kPartLen;
-  auto step = eals::heavy_step_kernel<LD, USER>;
-  CU(cudaFuncSetAttribute(step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eals::HeavySmem::kBytes));
+  auto step = s.slab == 256 ? eals::heavy_step_kernel<LD, USER, 256> : eals::heavy_step_kernel<LD, USER, 128>;
+  const int step_smem = (int)(s.slab == 256 ? eals::HeavySmem<256>::kBytes : eals::HeavySmem<128>::kBytes);
+  CU(cudaFuncSetAttribute(step, cudaFuncAttributeMaxDynamicSharedMemorySize, step_smem));
   if (!a.use_cache) {
-    eals::heavy_pred_kernel<LD><<<nu, eals::kBlkThreads, 0, m->stream>>>(a, hu, b.u0, s.pred);
+    eals::heavy_pred_kernel<LD><<<nu, eals::kBlkThreads, 0, m->stream>>>(a, hu, s.pred);
     OK(check_launch(m));
   }
   for (int fb = 0; fb <= nblocks; fb++) {
     if (fb == nblocks && !a.pc_out.n) break;   // last cache update: only when the symmetric cache keeps the result
-    step<<<nu, eals::kBlkThreads, eals::HeavySmem::kBytes, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
+    step<<<nu, s.slab, step_smem, m->stream>>>(a, hu, b.u0, fb, nblocks, s.pred, s.delta, part);
     OK(check_launch(m));
     if (fb == nblocks) break;
     eals::heavy_reduce_kernel<<<ngroups, eals::kBlkThreads, 0, m->stream>>>(part, hu, g0, b.u0, part2);
