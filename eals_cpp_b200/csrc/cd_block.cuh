@@ -75,6 +75,21 @@ __device__ __forceinline__ void stage_tile_rows(unsigned char* tile, const doubl
   }
 }
 
+// Blocks fb - 1 and fb of the same rows into two tiles with ONE pass over the row-pointer table
+// (heavy_step: the deferred cache update and the Gram pass need consecutive blocks of the same rows).
+__device__ __forceinline__ void stage_two_tiles(unsigned char* tile_prev, unsigned char* tile, const double* const* rowp_s,
+                                                int n, int n_pad, int fb, bool do_prev, bool do_cur, int tid, int nthreads) {
+  const int c = tid & 7;
+  const uint32_t col_bytes = (uint32_t)(fb * (kFB * 8) + c * 16);
+  for (int r = tid >> 3; r < n_pad; r += nthreads >> 3) {
+    const bool live = r < n;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(rowp_s[live ? r : 0]) + col_bytes;
+    const uint32_t dst = (uint32_t)(r * 128) + (uint32_t)(((c ^ r) & 7) << 4);
+    if (do_prev) cp_async16(tile_prev + dst, src - kFB * 8, live ? 16 : 0);
+    if (do_cur) cp_async16(tile + dst, src, live ? 16 : 0);
+  }
+}
+
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -958,8 +973,8 @@ struct HeavySmem {
 
 // Step fb of the batch: (1) if fb > 0, apply the cache update of block fb-1 (needs that block's
 // lines again); (2) if fb < nblocks, form the slab's partial Gram and right-hand side of block fb
-// (tensor cores) and write them to partials[slot].  Both tiles are requested up front (two cp.async
-// groups in flight), so a slab pays one memory round trip per step, not two; the slab descriptor is
+// (tensor cores) and write them to partials[slot].  Both tiles are requested up front in one pass
+// over the row pointers, so a slab pays one memory round trip per step, not two; the slab descriptor is
 // one 32-byte record in launch order, so the dependent chain is descriptor -> indices -> gather.
 // One nonzero per thread: SLAB threads per CTA (256: 3 CTAs/SM, 128: 6 CTAs/SM).
 template <int LD, bool USER, int SLAB>
@@ -997,16 +1012,10 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   if (fb > 0 && tid < 16) delta_s[tid] = delta[(size_t)ud.hrow * 16 + tid];
   __syncthreads();
 
+  stage_two_tiles(tile_prev, tile, rowp_s, n, n_pad, fb, fb > 0, fb < nblocks, tid, SLAB);
+  cp_async_commit();
   if (fb > 0) {
-    stage_tile_rows(tile_prev, rowp_s, n, n_pad, fb - 1, tid, SLAB);
-    cp_async_commit();
-  }
-  if (fb < nblocks) {
-    stage_tile_rows(tile, rowp_s, n, n_pad, fb, tid, SLAB);
-    cp_async_commit();
-  }
-  if (fb > 0) {
-    if (fb < nblocks) cp_async_wait<1>(); else cp_async_wait<0>();
+    cp_async_wait<0>();
     __syncthreads();
     if (tid < n) {
       double y[16];
@@ -1028,8 +1037,8 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
   }
   if (fb >= nblocks) return;
   z_s[tid] = tid < n ? wr - cw * pr : 0.0;
-  cp_async_wait<0>();
-  __syncthreads();
+  if (fb == 0) cp_async_wait<0>();
+  __syncthreads();   // z_s (and, for fb = 0, the tile) visible; every thread is done with tile_prev
 
   double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   gram_rhs_fragments(tile, c_s, z_s, warp * 32, min(warp * 32 + 32, n_pad), frag);
