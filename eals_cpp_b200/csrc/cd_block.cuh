@@ -451,15 +451,17 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// One CTA (a team of TW = 2, 4 or 8 warps) per row of up to 32*TW*MW nonzeros.  Thread t owns
-// nonzeros t, t+32*TW, ...; warp w
-// feeds tile rows [w*32*MW, (w+1)*32*MW) to the tensor cores (Gram + right-hand side, 5 tiles per 4
-// nonzeros).  The S.x term of the block is spread over ALL threads (thread = (factor, 1/16th of k))
-// and issued before the wait on the tile, so its loads overlap the gather; warp 0 then only runs
-// the 16-step multiply/shuffle/fma recurrence.
-// First version of this kernel (profiles r01b): 143 registers -> 1 CTA/SM, barrier stall 7.8 per
-// issue while warp 0 did the whole solve incl. 64 S loads per lane.  Now capped at 128 registers
-// (2 CTAs/SM up to 512 nonzeros).
+// One CTA (a team of TW warps) per row of up to 32*TW*MW nonzeros, MW nonzeros per thread: thread t
+// owns nonzeros t, t+32*TW, ...; warp w feeds tile rows [w*32*MW, (w+1)*32*MW) to the tensor cores
+// (Gram + right-hand side, 5 tiles per 4 nonzeros).  The S.x term of the block is spread over ALL
+// threads (thread = (factor, 1/16th of k)) and issued before the wait on the tile, so its loads
+// overlap the gather; warp 0 then only runs the 16-step multiply/shuffle/fma recurrence.
+// Used as <4, 2> for rows of 129..256 nonzeros (4 CTAs = 4 rows in flight per SM) and <8, 2> for
+// 257..512 (2 per SM).  What matters most is the number of ROWS in flight per SM, not the number of
+// warps per row: measured on c4, 129..256 as 8 warps x 1 nonzero (2 rows/SM, even with the next
+// tile prefetched under the solve) took 73 ms, as 4 warps x 2 nonzeros (4 rows/SM) 62 ms
+// (profiles/README.md r01i).  First version (r01b): 143 registers -> 1 CTA/SM, barrier stall 7.8 per
+// issue while warp 0 did the whole solve incl. 64 S loads per lane; now capped at 128 registers.
 // ---------------------------------------------------------------------------------------------
 template <int LD, int TW, int MW>
 struct RowBlockSmem {
@@ -670,222 +672,6 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       if (j < n) pc_store(a, p0 + j, pr[m]);
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Team kernel, second version: one CTA (TW = 2, 4, 8 or 16 warps) per row of up to 32*TW nonzeros,
-// ONE nonzero per thread.
-//
-// What the first version paid per factor block was a full memory round trip: the tile of block
-// fb + 1 could only be requested after the prediction-cache update of block fb had read the tile of
-// block fb again.  Here every thread copies its own nonzero's 16 values of the block into registers
-// when the tile arrives, so the tile buffer is free as soon as the tensor-core pass over it is done
-// and the gather of the next block runs underneath the cross-warp reduction, the 16-step solve and
-// the cache update (prefetch distance ~1000+ cycles, no second tile buffer).
-// ---------------------------------------------------------------------------------------------
-template <int LD, int TW>
-struct TeamSmem {
-  static constexpr int kT = TW * 32;
-  static constexpr int kParts = (kT / 16 < LD / 2) ? kT / 16 : LD / 2;   // S.x: threads = (factor, slice of k)
-  static constexpr size_t kTile = (size_t)kT * 128;
-  static constexpr size_t kBytes = kTile + (size_t)kT * (8 + 8 + 8) + (size_t)LD * 8 + (size_t)TW * kPartLen * 8 +
-                                   (256 + 16 + 16 + 16 + kParts * 16) * 8;
-};
-
-template <int LD, int TW, bool USER>
-__global__ void __launch_bounds__(TW * 32, (TW <= 8 ? 16 / TW : 1))
-cd_team_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  using Sm = TeamSmem<LD, TW>;
-  constexpr int kT = Sm::kT;
-  constexpr int kParts = Sm::kParts;
-  constexpr int kPer = LD / kParts;                       // k's per S.x thread (>= 2)
-  constexpr int kRedItems = kPartLen + 16;                // 208 partial sums + 16 S.x totals
-  constexpr int kRedIter = (kRedItems + kT - 1) / kT;
-  unsigned char* tile = smem;
-  const double** rowp_s = reinterpret_cast<const double**>(smem + Sm::kTile);
-  double* c_s = reinterpret_cast<double*>(smem + Sm::kTile + (size_t)kT * 8);
-  double* z_s = c_s + kT;
-  double* x_s = z_s + kT;
-  double* slots = x_s + LD;
-  double* Gs = slots + TW * kPartLen;
-  double* Pt = Gs + 256;
-  double* Tt = Pt + 16;
-  double* delta_s = Tt + 16;
-  double* tpart = delta_s + 16;    // [kParts][16 factors]
-
-  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-  const int row = order[first + blockIdx.x];
-  const int64_t p0 = a.ptr[row];
-  const int n = (int)(a.ptr[row + 1] - p0);
-  const int n_pad = (n + 3) & ~3;
-  const int grow = a.row_base + row;
-  double* xrow = a.X + (size_t)grow * LD;
-  const int K = a.K;
-  const double wi_row = USER ? 0.0 : a.Wi[grow];
-  const double g = USER ? 1.0 : wi_row;
-  const bool mine = tid < n;
-
-  double pr = 0.0, cw = 0.0, wr = 0.0;
-  if (mine) {
-    const int id = a.idx[p0 + tid];
-    rowp_s[tid] = a.Y + (size_t)id * LD;
-    const double w = a.val ? a.val[p0 + tid] : 1.0;
-    wr = w * w;
-    cw = w - (USER ? a.Wi[id] : wi_row);
-    if (a.use_cache) pr = a.pc_in[p0 + tid];
-  }
-  c_s[tid] = cw;
-  z_s[tid] = 0.0;
-  for (int k = tid; k < LD; k += kT) x_s[k] = xrow[k];
-  __syncthreads();
-
-  if (!a.use_cache) {
-    // prediction cache from scratch, p_j = <x, y_j>: 8 lanes per nonzero straight from global memory
-    // (whole 128-byte lines per 8 lanes, all loads of a thread independent)
-    const int g8 = tid >> 3, gl = tid & 7;
-    for (int j0 = 0; j0 < n; j0 += kT / 8) {
-      const int j = j0 + g8;
-      double acc0 = 0.0, acc1 = 0.0;
-      if (j < n) {
-        const double* yrow = rowp_s[j];
-#pragma unroll
-        for (int c = 0; c < LD; c += kFB) {
-          const double2 d = ldg2(yrow + c + gl * 2);
-          acc0 += x_s[c + gl * 2] * d.x;
-          acc1 += x_s[c + gl * 2 + 1] * d.y;
-        }
-      }
-      double acc = acc0 + acc1;
-      acc += __shfl_xor_sync(kFullMask, acc, 1);
-      acc += __shfl_xor_sync(kFullMask, acc, 2);
-      acc += __shfl_xor_sync(kFullMask, acc, 4);
-      if (j < n && gl == 0) z_s[j] = acc;
-    }
-    __syncthreads();
-    if (mine) pr = z_s[tid];
-    __syncthreads();
-  }
-
-  const int nblocks = (K + kFB - 1) / kFB;
-  const int w_r0 = warp * 32, w_r1 = min(warp * 32 + 32, n_pad);
-  const int tf = tid & 15, tpart_id = tid >> 4;
-
-  stage_tile_rows(tile, rowp_s, n, n_pad, 0, tid, kT);
-  cp_async_commit();
-  for (int fb = 0; fb < nblocks; fb++) {
-    const int f0 = fb * kFB;
-    if (mine) z_s[tid] = wr - cw * pr;
-    if (tpart_id < kParts) {   // partial t_f = sum over this thread's k's of x_k S[k][f0+f] (S symmetric)
-      const double* __restrict__ Sc = a.S + (size_t)(tpart_id * kPer) * LD + f0 + tf;
-      double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-      for (int k = 0; k < kPer; k += 2) {
-        t0 += x_s[tpart_id * kPer + k] * __ldg(Sc + (size_t)k * LD);
-        t1 += x_s[tpart_id * kPer + k + 1] * __ldg(Sc + (size_t)(k + 1) * LD);
-      }
-      tpart[tpart_id * 16 + tf] = t0 + t1;
-    }
-    // the S_BB entries the reduction adds: requested now, consumed after the tensor-core pass
-    double s_bb[kRedIter];
-#pragma unroll
-    for (int q = 0; q < kRedIter; q++) {
-      const int i = tid + q * kT;
-      s_bb[q] = 0.0;
-      if (i < 192) {
-        const int t = i >> 6, l = (i & 63) >> 1, ii = i & 1;
-        int rw = l >> 2, cl = 2 * (l & 3) + ii;
-        if (t >= 1) rw += 8;
-        if (t == 2) cl += 8;
-        s_bb[q] = __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
-      }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-
-    double y[16];
-    if (mine) load_tile_row(tile, tid, y);
-    double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    gram_rhs_fragments(tile, c_s, z_s, w_r0, w_r1, frag);
-    double* slot = slots + warp * kPartLen;
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      slot[t * 64 + lane * 2] = frag[2 * t];
-      slot[t * 64 + lane * 2 + 1] = frag[2 * t + 1];
-    }
-    if ((lane & 3) == 0) {
-      slot[192 + (lane >> 2)] = frag[6];
-      slot[200 + (lane >> 2)] = frag[8];
-    }
-    __syncthreads();
-    if (fb + 1 < nblocks) {   // the tile is consumed: fetch the next block underneath the solve
-      stage_tile_rows(tile, rowp_s, n, n_pad, fb + 1, tid, kT);
-      cp_async_commit();
-    }
-#pragma unroll
-    for (int q = 0; q < kRedIter; q++) {
-      const int i = tid + q * kT;
-      if (i < kPartLen) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < TW; w++) s += slots[w * kPartLen + i];
-        if (i < 192) {   // H = G + g S_BB
-          const int t = i >> 6, l = (i & 63) >> 1, ii = i & 1;
-          int rw = l >> 2, cl = 2 * (l & 3) + ii;
-          if (t >= 1) rw += 8;
-          if (t == 2) cl += 8;
-          s += g * s_bb[q];
-          Gs[rw * 16 + cl] = s;
-          if (t == 1) Gs[cl * 16 + rw] = s;
-        } else {
-          Pt[i - 192] = s;
-        }
-      } else if (i < kRedItems) {
-        const int ff = i - kPartLen;
-        double s = 0.0;
-#pragma unroll
-        for (int q2 = 0; q2 < kParts; q2++) s += tpart[q2 * 16 + ff];
-        Tt[ff] = s;
-      }
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int ff = lane & 15;
-      double h[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + ff];
-      const double hff = Gs[ff * 16 + ff];
-      const double xf = x_s[f0 + ff];
-      double numer = Pt[ff] - g * Tt[ff] + xf * hff;
-      const double rden = 1.0 / (hff + a.reg);
-#pragma unroll
-      for (int sidx = 0; sidx < 16; sidx++) {
-        const double d = numer * rden - xf;
-        const double ds = __shfl_sync(kFullMask, d, sidx);
-        if (ff > sidx) numer -= ds * h[sidx];
-      }
-      const double xnew = numer * rden;
-      if (lane < 16) {
-        const bool livef = f0 + ff < K;
-        if (livef) x_s[f0 + ff] = xnew;
-        delta_s[ff] = livef ? xnew - xf : 0.0;
-      }
-    }
-    __syncthreads();
-    if (mine) {
-      double a0 = pr, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) {
-        a0 += delta_s[e] * y[e];
-        a1 += delta_s[e + 1] * y[e + 1];
-        a2 += delta_s[e + 2] * y[e + 2];
-        a3 += delta_s[e + 3] * y[e + 3];
-      }
-      pr = (a0 + a1) + (a2 + a3);
-    }
-  }
-  for (int k = tid; k < K; k += kT) store_row_value(a, (size_t)grow * LD + k, x_s[k]);
-  if (a.pc_out.n && mine) pc_store(a, p0 + tid, pr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -759,16 +759,6 @@ int launch_cd_row_block(eals_model* m, const CdSide& a, const int32_t* order, in
   return check_launch(m);
 }
 
-template <int LD, int TW, bool USER>
-int launch_cd_team(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
-  if (count <= 0) return EALS_OK;
-  using Sm = eals::TeamSmem<LD, TW>;
-  auto kern = eals::cd_team_kernel<LD, TW, USER>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sm::kBytes));
-  kern<<<count, TW * 32, Sm::kBytes, m->stream>>>(a, order, first);
-  return check_launch(m);
-}
-
 eals::HeavyUnits heavy_units(const Side& s) {
   eals::HeavyUnits hu;
   hu.units = nullptr;
@@ -828,7 +818,7 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     if (n <= 32) return launch_cd_warp_block<LD, 1, USER>(m, a, one, 0, 1);
     if (n <= 64) return launch_cd_warp_block<LD, 2, USER>(m, a, one, 0, 1);
     if (n <= 128) return launch_cd_warp_block<LD, 4, USER>(m, a, one, 0, 1);
-    if (n <= 256) return launch_cd_team<LD, 8, USER>(m, a, one, 0, 1);
+    if (n <= 256) return launch_cd_row_block<LD, 4, 2, USER>(m, a, one, 0, 1);
     return launch_cd_row_block<LD, 8, 2, USER>(m, a, one, 0, 1);
   }
   // heavy rows first: their launch chain is the longest
@@ -838,7 +828,7 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   toc(m, t0);
   tic(m, t0 + 1);
   OK((launch_cd_row_block<LD, 8, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));   // 257..512
-  OK((launch_cd_team<LD, 8, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));           // 129..256
+  OK((launch_cd_row_block<LD, 4, 2, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));   // 129..256
   toc(m, t0 + 1);
   tic(m, t0 + 2);
   // EALS_WARP_SEQ=1: the plain sequential form (one reduction + one divide per factor) for A/B runs;
