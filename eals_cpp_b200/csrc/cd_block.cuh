@@ -138,7 +138,7 @@ struct WarpBlockSmem {
   static constexpr size_t kTile = (size_t)kRows * 128;
   // tile | row pointers | c | z | x | Gs[256] | Pt[16] | delta[16]
   static constexpr size_t kBytesPerWarp = kTile + (size_t)kRows * (8 + 8 + 8) + (size_t)LD * 8 + (256 + 16 + 16) * 8;
-  static constexpr int kMaxWarps = MAXM == 1 ? 16 : (MAXM == 2 ? 11 : 6);
+  static constexpr int kMaxWarps = MAXM == 1 ? 16 : (MAXM == 2 ? 11 : (MAXM == 3 ? 8 : 6));
 };
 
 // Gram + right-hand-side fragments of tile rows [0, r1): frag[0..5] as gram_fragments, frag[6..7] =

@@ -106,14 +106,14 @@ int dev_reserve(T** p, size_t* cap, size_t n) {
 }
 
 // Buckets of owned rows by length.  Bucket 0 = empty rows (skipped: MF_fastALS.cpp:249,344).
-// 1..3: warp per row (1/2/4 nonzeros per lane); 4..6: one CTA per row, blocked CD (1/2/4 nonzeros
-// per thread); 7: heavy rows, split into slabs.
-constexpr int kNumBuckets = 8;
-// bucket 6 is kept empty: measured on c4, rows of 513..1024 nonzeros run faster through the slab
-// pipeline (0.5 ns/nnz) than as one CTA per SM (1 ns/nnz).
-constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 128, 256, 512, 512, 0x7fffffff};
-constexpr int kMidBucket = 4;     // first one-CTA-per-row bucket
-constexpr int kHeavyBucket = 7;
+// 1..4: one warp per row (1/2/3/4 nonzeros per lane); 5..7: one CTA per row (4 warps x 2, 4 x 3,
+// 8 x 2 nonzeros per thread); 8: heavy rows, split into slabs.  The finer the buckets, the closer a
+// row's shared-memory tile is to its real length and the more rows an SM holds in flight.
+// Measured on c4: rows of 513..1024 nonzeros run faster through the slab pipeline than as one CTA.
+constexpr int kNumBuckets = 9;
+constexpr int kBucketMax[kNumBuckets] = {0, 32, 64, 96, 128, 256, 384, 512, 0x7fffffff};
+constexpr int kMidBucket = 5;     // first one-CTA-per-row bucket
+constexpr int kHeavyBucket = 8;
 // Heavy rows per launch group.  Measured on c4 (profiles/README.md r01b): launch granularity matters
 // more than keeping one factor block of the batch L2-resident (384k nnz: 363 ms, 24M nnz: 204 ms).
 // Since the slabs of a batch are launched in neighbour order (HeavyUnits::launch) the bigger the batch
@@ -132,7 +132,7 @@ struct Side {
   double* val = nullptr;
   int32_t* order = nullptr;           // owned-row ids grouped by bucket, ascending id inside
   int first[kNumBuckets + 1] = {0};   // bucket b = order[first[b] .. first[b+1])
-  // heavy rows (bucket 7): row h = order[first[7] + h], longest first
+  // heavy rows (bucket kHeavyBucket): row h = order[first[kHeavyBucket] + h], longest first
   int n_hrows = 0, n_units = 0, max_batch_units = 0;
   int64_t heavy_nnz = 0;
   eals::UnitDesc* units_canon = nullptr;    // slab descriptors, canonical order (row by row)
@@ -817,8 +817,10 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
     CU(cudaMemcpyAsync(one, &only_row, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
     if (n <= 32) return launch_cd_warp_block<LD, 1, USER>(m, a, one, 0, 1);
     if (n <= 64) return launch_cd_warp_block<LD, 2, USER>(m, a, one, 0, 1);
+    if (n <= 96) return launch_cd_warp_block<LD, 3, USER>(m, a, one, 0, 1);
     if (n <= 128) return launch_cd_warp_block<LD, 4, USER>(m, a, one, 0, 1);
     if (n <= 256) return launch_cd_row_block<LD, 4, 2, USER>(m, a, one, 0, 1);
+    if (n <= 384) return launch_cd_row_block<LD, 4, 3, USER>(m, a, one, 0, 1);
     return launch_cd_row_block<LD, 8, 2, USER>(m, a, one, 0, 1);
   }
   // heavy rows first: their launch chain is the longest
@@ -827,19 +829,21 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   for (const HeavyBatch& b : s.batches) OK((run_heavy_batch<LD, USER>(m, s, a, b, true)));
   toc(m, t0);
   tic(m, t0 + 1);
-  OK((launch_cd_row_block<LD, 8, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));   // 257..512
-  OK((launch_cd_row_block<LD, 4, 2, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));   // 129..256
+  OK((launch_cd_row_block<LD, 8, 2, USER>(m, a, s.order, s.first[7], s.first[8] - s.first[7])));   // 385..512
+  OK((launch_cd_row_block<LD, 4, 3, USER>(m, a, s.order, s.first[6], s.first[7] - s.first[6])));   // 257..384
+  OK((launch_cd_row_block<LD, 4, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));   // 129..256
   toc(m, t0 + 1);
   tic(m, t0 + 2);
   // EALS_WARP_SEQ=1: the plain sequential form (one reduction + one divide per factor) for A/B runs;
   // measured on c4 it is 2.6x slower than the blocked form (profiles/README.md r01h)
   static const bool seq = getenv("EALS_WARP_SEQ") && getenv("EALS_WARP_SEQ")[0] == '1';
   if (seq) {
-    OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+    OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[5] - s.first[3])));
     OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
     OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
   } else {   // one warp per row up to 128 nonzeros: no CTA barrier anywhere in the row loop
-    OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+    OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
+    OK((launch_cd_warp_block<LD, 3, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
     OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
     OK((launch_cd_warp_block<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
   }
