@@ -127,6 +127,13 @@ __device__ __forceinline__ void load_tile_row(const unsigned char* tile, int r, 
 // row stride makes both the row walk (element of the block's transpose) and the column walk
 // conflict-free across the 16 factor lanes.
 constexpr int kSBlk = 16 * 17;
+// The 16 x 16 block system H of one row, lower triangle only, row stride 17: the fragment lanes store
+// their 8 x 8 tiles (T00, T10, T11) as they hold them and solve lane f reads ROW f (H is symmetric and
+// step f only needs H[f][s], s <= f) — conflict-free.  The first layout (stride 16 plus a transposed copy
+// of T10 for column reads) made every store an 8-way bank conflict: ~100 of the 455 shared-memory
+// wavefronts per row and block of the short-row kernel, which is shared-memory bound (profiles r01h).
+constexpr int kGsStride = 17;
+constexpr int kGsLen = 16 * kGsStride;
 __host__ __device__ constexpr int s_tri(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
 
 template <int LD, int MAXM>
@@ -136,9 +143,9 @@ struct WarpBlockSmem {
   static constexpr int kRows = 32 * MAXM;
   static constexpr size_t kS = kSInSmem ? (size_t)s_tri(kNB, 0) * kSBlk * 8 : 0;
   static constexpr size_t kTile = (size_t)kRows * 128;
-  // tile | row pointers | c | z | x | Gs[256] | Pt[16] | delta[16]
-  static constexpr size_t kBytesPerWarp = kTile + (size_t)kRows * (8 + 8 + 8) + (size_t)LD * 8 + (256 + 16 + 16) * 8;
-  static constexpr int kMaxWarps = MAXM == 1 ? 16 : (MAXM == 2 ? 11 : (MAXM == 3 ? 8 : 6));
+  // tile | row pointers | x | Gs | Pt[16] | delta[16]
+  static constexpr size_t kBytesPerWarp = kTile + (size_t)kRows * 8 + (size_t)LD * 8 + (kGsLen + 16 + 16) * 8;
+  static constexpr int kMaxWarps = MAXM == 1 ? 16 : (MAXM == 2 ? 12 : (MAXM == 3 ? 9 : 7));
 };
 
 // Gram + right-hand-side fragments of tile rows [0, r1): frag[0..5] as gram_fragments, frag[6..7] =
@@ -156,6 +163,32 @@ __device__ __forceinline__ void gram_rhs_fragments(const unsigned char* tile, co
     const double a1 = *reinterpret_cast<const double*>(rowp + ((((uint32_t)(4 + (e0 >> 1))) ^ sw) << 4));
     const double cj = c_s[r];
     const double zj = e0 == 0 ? z_s[r] : 0.0;
+    const double b0 = cj * a0, b1 = cj * a1;
+    dmma_884(frag[0], frag[1], a0, b0);
+    dmma_884(frag[2], frag[3], a1, b0);
+    dmma_884(frag[4], frag[5], a1, b1);
+    dmma_884(frag[6], frag[7], a0, zj);
+    dmma_884(frag[8], frag[9], a1, zj);
+  }
+}
+
+// The same for tile rows [r0, r0 + 32) with c_j / z_j taken from the owning lanes' registers (row
+// r0 + l belongs to lane l of this warp): one shuffle each instead of a shared-memory array — the
+// warp-per-row kernels spend their shared memory on tiles (= rows in flight), not on scalars.
+__device__ __forceinline__ void gram_rhs_fragments_reg(const unsigned char* tile, double c_lane, double z_lane,
+                                                       int r0, int r1, double (&frag)[10]) {
+  const int lane = lane_id();
+  const int rr = lane & 3, e0 = lane >> 2;
+  const uint32_t off_lo = (uint32_t)(rr * 128 + ((e0 & 1) << 3));
+  for (int j0 = r0; j0 < r1; j0 += 4) {
+    const int r = j0 + rr;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const unsigned char* rowp = tile + (size_t)j0 * 128 + off_lo;
+    const double a0 = *reinterpret_cast<const double*>(rowp + ((((uint32_t)(e0 >> 1)) ^ sw) << 4));
+    const double a1 = *reinterpret_cast<const double*>(rowp + ((((uint32_t)(4 + (e0 >> 1))) ^ sw) << 4));
+    const double cj = __shfl_sync(kFullMask, c_lane, (j0 - r0) + rr);
+    const double zq = __shfl_sync(kFullMask, z_lane, (j0 - r0) + rr);
+    const double zj = e0 == 0 ? zq : 0.0;
     const double b0 = cj * a0, b1 = cj * a1;
     dmma_884(frag[0], frag[1], a0, b0);
     dmma_884(frag[2], frag[3], a1, b0);
@@ -190,11 +223,9 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
   unsigned char* base = smem + Sm::kS + (size_t)warp * Sm::kBytesPerWarp;
   unsigned char* tile = base;
   const double** rowp_s = reinterpret_cast<const double**>(base + Sm::kTile);
-  double* c_s = reinterpret_cast<double*>(base + Sm::kTile + (size_t)Sm::kRows * 8);
-  double* z_s = c_s + Sm::kRows;
-  double* x_s = z_s + Sm::kRows;
+  double* x_s = reinterpret_cast<double*>(base + Sm::kTile + (size_t)Sm::kRows * 8);
   double* Gs = x_s + LD;
-  double* Pt = Gs + 256;
+  double* Pt = Gs + kGsLen;
   double* delta_s = Pt + 16;
 
   const int K = a.K;
@@ -272,8 +303,6 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
         cw[m] = w - (USER ? wi_n[m] : wi_row);
         if (a.use_cache) pr[m] = pc_n[m];
       }
-      c_s[j] = cw[m];
-      z_s[j] = 0.0;
     }
 #pragma unroll
     for (int i = 0; i < XN; i++)
@@ -308,11 +337,6 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
     for (int fb = 0; fb < nblocks; fb++) {
       const int f0 = fb * kFB;
       if (fb < 4) fetch_next(fb, slot + stride);
-#pragma unroll
-      for (int m = 0; m < MAXM; m++) {
-        const int j = m * 32 + lane;
-        if (j < n) z_s[j] = wr[m] - cw[m] * pr[m];
-      }
       // S.x for this block while the tile is in flight: t_f = sum_k x_k S[k][f0+f]; lane = (f, half
       // of the k blocks)
       double tsum;
@@ -367,7 +391,9 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
       __syncwarp();
 
       double frag[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      gram_rhs_fragments(tile, c_s, z_s, 0, n_pad, frag);
+#pragma unroll
+      for (int m = 0; m < MAXM; m++)   // z_j = w_j r_j - c_j p_j; rows beyond n have c = z = 0
+        gram_rhs_fragments_reg(tile, cw[m], wr[m] - cw[m] * pr[m], m * 32, min(m * 32 + 32, n_pad), frag);
       // H = G + g S_BB, full symmetric 16 x 16, and P
 #pragma unroll
       for (int t = 0; t < 3; t++) {
@@ -379,8 +405,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
           const double sbb = Sm::kSInSmem ? S_s[s_tri(fb, fb) * kSBlk + rw * 17 + cl]
                                           : __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
           const double v = frag[2 * t + ii] + g * sbb;
-          Gs[rw * 16 + cl] = v;
-          if (t == 1) Gs[cl * 16 + rw] = v;
+          Gs[rw * kGsStride + cl] = v;
         }
       }
       if ((lane & 3) == 0) {
@@ -392,8 +417,8 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
       // in-block Gauss-Seidel, lane f (both half-warps compute the same thing)
       double h[16];
 #pragma unroll
-      for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + f];
-      const double hff = Gs[f * 16 + f];
+      for (int k = 0; k < 16; k++) h[k] = Gs[f * kGsStride + k];   // row f = column f (only k < f is used)
+      const double hff = Gs[f * kGsStride + f];
       const double xf = x_s[f0 + f];
       double numer = Pt[f] - g * tsum + xf * hff;
       const double rden = 1.0 / (hff + a.reg);
@@ -472,7 +497,7 @@ struct RowBlockSmem {
   static constexpr size_t kCZ = (size_t)kRows * 16;           // c and z
   static constexpr size_t kX = (size_t)LD * 8;
   static constexpr size_t kSlots = (size_t)TW * kPartLen * 8;
-  static constexpr size_t kSmall = (256 + 16 + 16 + 16 + 16 * 16) * 8;   // Gs, Pt, Tt, delta, tpart[<=16][16]
+  static constexpr size_t kSmall = (kGsLen + 16 + 16 + 16 + 16 * 16) * 8;   // Gs, Pt, Tt, delta, tpart[<=16][16]
   static constexpr size_t kBytes = kTile + kIdx + kCZ + kX + kSlots + kSmall;
 };
 
@@ -491,7 +516,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
   double* x_s = z_s + Sm::kRows;
   double* slots = x_s + LD;
   double* Gs = slots + TW * kPartLen;
-  double* Pt = Gs + 256;
+  double* Pt = Gs + kGsLen;
   double* Tt = Pt + 16;
   double* delta_s = Tt + 16;
   double* tpart = delta_s + 16;    // [kParts][16 factors]
@@ -599,8 +624,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
           if (t >= 1) rw += 8;
           if (t == 2) cl += 8;
           s += g * __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
-          Gs[rw * 16 + cl] = s;
-          if (t == 1) Gs[cl * 16 + rw] = s;
+          Gs[rw * kGsStride + cl] = s;
         } else {
           Pt[i - 192] = s;
         }
@@ -617,8 +641,8 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       const int ff = lane & 15;
       double h[16];
 #pragma unroll
-      for (int k = 0; k < 16; k++) h[k] = Gs[k * 16 + ff];
-      const double hff = Gs[ff * 16 + ff];
+      for (int k = 0; k < 16; k++) h[k] = Gs[ff * kGsStride + k];
+      const double hff = Gs[ff * kGsStride + ff];
       const double xf = x_s[f0 + ff];
       double numer = Pt[ff] - g * Tt[ff] + xf * hff;
       const double rden = 1.0 / (hff + a.reg);
@@ -869,7 +893,7 @@ __global__ void __launch_bounds__(kBlkThreads)
 heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int g0, int fb, const double* __restrict__ partials,
                    double* __restrict__ delta) {
   __shared__ double x_s[LD];
-  __shared__ double Gs[256];
+  __shared__ double Gs[kGsLen];
   __shared__ double Pt[16];
   __shared__ double Tt[16];
   __shared__ double tpart[16][16];
@@ -921,8 +945,7 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int g0, int fb, const double
       if (t >= 1) rw += 8;
       if (t == 2) cl += 8;
       sum += g * __ldg(a.S + (size_t)(f0 + rw) * LD + f0 + cl);
-      Gs[rw * 16 + cl] = sum;
-      if (t == 1) Gs[cl * 16 + rw] = sum;
+      Gs[rw * kGsStride + cl] = sum;
     } else {
       Pt[tid - 192] = sum;
     }
@@ -939,8 +962,8 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int g0, int fb, const double
     const int ff = lane & 15;
     double hcol[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) hcol[k] = Gs[k * 16 + ff];
-    const double hff = Gs[ff * 16 + ff];
+    for (int k = 0; k < 16; k++) hcol[k] = Gs[ff * kGsStride + k];
+    const double hff = Gs[ff * kGsStride + ff];
     const double xf = x_s[f0 + ff];
     double numer = Pt[ff] - g * Tt[ff] + xf * hff;
     const double rden = 1.0 / (hff + a.reg);
