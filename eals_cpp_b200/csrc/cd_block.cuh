@@ -265,7 +265,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
         if (j < n_n) {
           id_n[m] = a.idx[p0_n + j];
           if (a.use_cache) pc_n[m] = a.pc_in[p0_n + j];
-          if (a.pc_out.n) g_n[m] = a.pc_map[p0_n + j];
+          if (a.pc_out.n && !a.pc_stage) g_n[m] = a.pc_map[p0_n + j];
         }
       }
     } else if (USER) {
@@ -467,7 +467,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
 #pragma unroll
       for (int m = 0; m < MAXM; m++) {
         const int j = m * 32 + lane;
-        if (j < n) pc_store_at(a, gpos[m], pr[m]);
+        if (j < n) pc_emit(a, p0 + j, gpos[m], pr[m]);
       }
     }
     for (int st = stages_in_loop; st < 4; st++) fetch_next(st, slot + stride);   // K < 64: finish the chain here

@@ -61,6 +61,10 @@ struct CdSide {
   const double* pc_in;     // nullptr: no cache
   const uint32_t* pc_map;  // per local nonzero: its global position in the other orientation
   PcOut pc_out;
+  // Multi-rank: final predictions are first written here in THIS side's nonzero order (coalesced) and
+  // routed to their owners afterwards by pc_route_kernel in destination order — scattered 8-byte
+  // stores straight into peer memory were far slower than the gather they replace (r01f).
+  double* pc_stage;        // nullptr: store directly through pc_map / pc_out
   int use_cache;           // 1: pc_in is valid on entry, read it instead of recomputing
   PeerSet peers;        // other ranks' replicas of X (n = 0: none)
 };
@@ -78,12 +82,29 @@ __device__ __forceinline__ void pc_store_at(const CdSide& a, uint32_t g, double 
   a.pc_out.base[r][g - a.pc_out.bound[r]] = v;
 }
 
+// The final prediction of local nonzero local_pos (its position g in the other orientation already
+// looked up, or not needed when the values are staged).
+__device__ __forceinline__ void pc_emit(const CdSide& a, int64_t local_pos, uint32_t g, double v) {
+  if (a.pc_stage) a.pc_stage[local_pos] = v;
+  else pc_store_at(a, g, v);
+}
+
 __device__ __forceinline__ void pc_store(const CdSide& a, int64_t local_pos, double v) {
-  const uint32_t g = a.pc_map[local_pos];
+  if (a.pc_stage) a.pc_stage[local_pos] = v;
+  else pc_store_at(a, a.pc_map[local_pos], v);
+}
+
+// Second phase of the staged scheme: thread k moves the k-th value in DESTINATION order
+// (route_dst ascending, so neighbouring threads write neighbouring addresses of the same peer).
+__global__ void pc_route_kernel(const double* __restrict__ stage, const uint32_t* __restrict__ route_src,
+                                const uint32_t* __restrict__ route_dst, int64_t n, PcOut out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t g = route_dst[k];
   int r = 0;
 #pragma unroll
-  for (int t = 1; t < 8; t++) r += (t < a.pc_out.n && g >= a.pc_out.bound[t]) ? 1 : 0;
-  a.pc_out.base[r][g - a.pc_out.bound[r]] = v;
+  for (int t = 1; t < 8; t++) r += (t < out.n && g >= out.bound[t]) ? 1 : 0;
+  out.base[r][g - out.bound[r]] = stage[route_src[k]];
 }
 
 // ---------------------------------------------------------------------------------------------

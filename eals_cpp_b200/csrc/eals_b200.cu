@@ -193,6 +193,11 @@ struct eals_model {
   uint32_t* map_u = nullptr;     // owned CSR nonzero -> global CSC position of the same nonzero
   uint32_t* map_i = nullptr;     // owned CSC nonzero -> global CSR position
   size_t cap_pc_u = 0, cap_pc_i = 0, cap_map_u = 0, cap_map_i = 0;
+  // multi-rank: staged routing of the final predictions (see CdSide::pc_stage)
+  double *pc_stage_u = nullptr, *pc_stage_i = nullptr;
+  uint32_t *route_src_u = nullptr, *route_dst_u = nullptr, *route_src_i = nullptr, *route_dst_i = nullptr;
+  size_t cap_stage_u = 0, cap_stage_i = 0, cap_rsrc_u = 0, cap_rdst_u = 0, cap_rsrc_i = 0, cap_rdst_i = 0;
+  bool routed = false;
   eals::PcOut out_to_items = {}, out_to_users = {};   // where the other side's caches live (all ranks)
   int n_ranks = 1, rank = 0;
   bool pc_attached = false;      // caches usable: single rank, or both peers' cache sets mapped
@@ -291,6 +296,34 @@ __global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz
   if (q < nnz && perm[q] == 0xffffffffu) atomicExch(bad, 1);
 }
 
+__global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) v[t] = (uint32_t)t;
+}
+
+// Destination order of one side's nonzeros: route_dst = the map values ascending, route_src = the local
+// positions they belong to (cub radix sort, once per matrix).
+int build_routes(eals_model* m, const uint32_t* map, int64_t n, double** stage, size_t* cap_stage,
+                 uint32_t** rsrc, size_t* cap_rsrc, uint32_t** rdst, size_t* cap_rdst) {
+  OK(dev_reserve(stage, cap_stage, (size_t)n));
+  OK(dev_reserve(rsrc, cap_rsrc, (size_t)n));
+  OK(dev_reserve(rdst, cap_rdst, (size_t)n));
+  if (n == 0) return EALS_OK;
+  if (n >= 0x7fffffffLL) return fail(EALS_ERR_UNSUPPORTED, "too many nonzeros per rank for the routed prediction cache");
+  uint32_t* iota = reinterpret_cast<uint32_t*>(*stage);   // scratch: the staging buffer is not live yet
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(iota, n);
+  OK(check_launch(m));
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, map, *rdst, iota, *rsrc, (int)n, 0, 32, m->stream);
+  void* tmp = nullptr;
+  CU(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+  const cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, map, *rdst, iota, *rsrc, (int)n, 0, 32, m->stream);
+  cudaStreamSynchronize(m->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(EALS_ERR_CUDA, "route sort -> %s", cudaGetErrorString(e));
+  return EALS_OK;
+}
+
 // Unmap the other ranks' prediction caches (multi-rank models).
 void close_pc_peers(eals_model* m, eals::PcOut& out, bool& attached_flag) {
   for (int r = 0; r < out.n; r++)
@@ -379,6 +412,13 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   m->out_to_users.base[me] = m->pc_u;
   m->pc_attached = single;
   tm.lap("pred cache: position maps");
+  m->routed = false;
+  if (multi && !(getenv("EALS_PC_ROUTE") && getenv("EALS_PC_ROUTE")[0] == '0')) {
+    OK(build_routes(m, m->map_u, nu, &m->pc_stage_u, &m->cap_stage_u, &m->route_src_u, &m->cap_rsrc_u, &m->route_dst_u, &m->cap_rdst_u));
+    OK(build_routes(m, m->map_i, ni, &m->pc_stage_i, &m->cap_stage_i, &m->route_src_i, &m->cap_rsrc_i, &m->route_dst_i, &m->cap_rdst_i));
+    m->routed = true;
+    tm.lap("pred cache: routes");
+  }
   m->pcache_on = true;
   if (const char* e = getenv("EALS_PRED_REFRESH_EVERY")) m->pred_refresh_every = atoi(e);
   return EALS_OK;
@@ -863,7 +903,7 @@ int sweep(eals_model* m, bool user, int only_row) {
   a.row_base = s.row_base;
   a.K = m->K;
   a.reg = m->p.reg;
-  a.pc_in = nullptr; a.pc_map = nullptr; a.pc_out = eals::PcOut{}; a.use_cache = 0;
+  a.pc_in = nullptr; a.pc_map = nullptr; a.pc_out = eals::PcOut{}; a.use_cache = 0; a.pc_stage = nullptr;
   a.peers = user ? m->peersU : m->peersV;
   if (only_row >= 0) {
     m->pc_u_valid = m->pc_i_valid = false;   // a single-row update changes factors behind the cache's back
@@ -874,6 +914,7 @@ int sweep(eals_model* m, bool user, int only_row) {
     a.pc_in = user ? m->pc_u : m->pc_i;
     a.pc_map = user ? m->map_u : m->map_i;
     a.pc_out = user ? m->out_to_items : m->out_to_users;
+    if (m->routed) a.pc_stage = user ? m->pc_stage_u : m->pc_stage_i;
     a.use_cache = in_valid ? 1 : 0;
     m->sweeps_since_fresh = in_valid ? m->sweeps_since_fresh + 1 : 0;
     in_valid = false;    // this side's cache describes the factors BEFORE this sweep
@@ -881,6 +922,11 @@ int sweep(eals_model* m, bool user, int only_row) {
   }
   if (user) { DISPATCH_LD(m->LD, OK((launch_cd<LD, true>(m, s, a, only_row)))); }
   else      { DISPATCH_LD(m->LD, OK((launch_cd<LD, false>(m, s, a, only_row)))); }
+  if (a.pc_stage && s.nnz > 0) {   // second phase: staged predictions to their owners, in destination order
+    eals::pc_route_kernel<<<(unsigned)((s.nnz + 255) / 256), 256, 0, m->stream>>>(
+        a.pc_stage, user ? m->route_src_u : m->route_src_i, user ? m->route_dst_u : m->route_dst_i, s.nnz, a.pc_out);
+    OK(check_launch(m));
+  }
   return sync_if_debug(m);
 }
 
@@ -1233,6 +1279,8 @@ int eals_destroy(eals_model* m) {
   cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
   cudaFree(m->terms); cudaFree(m->partials); cudaFree(m->flags);
   cudaFree(m->pc_u); cudaFree(m->pc_i); cudaFree(m->map_u); cudaFree(m->map_i);
+  cudaFree(m->pc_stage_u); cudaFree(m->pc_stage_i);
+  cudaFree(m->route_src_u); cudaFree(m->route_dst_u); cudaFree(m->route_src_i); cudaFree(m->route_dst_i);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);

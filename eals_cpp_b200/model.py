@@ -216,10 +216,10 @@ class MF_fastALS:
             return
         dev = f"cuda:{self.device}"
         shared = [_lib.BUF_U, _lib.BUF_V]
-        # Sharing the prediction caches across ranks is OFF by default: measured on 2 x B200 (c4) the
-        # scattered 8-byte peer stores of the item sweep cost far more than the gather pass they save
-        # (item sweep 164 -> 699 ms); see profiles/README.md r01f.
-        if os.environ.get("EALS_PEER_PRED_CACHE", "0") == "1" and self._pred_cache_everywhere():
+        # The prediction caches are shared across ranks too: a sweep stages its final predictions locally
+        # and a second kernel routes them to their owners in destination order (EALS_PC_ROUTE=0: scattered
+        # 8-byte peer stores straight from the sweep kernels, measured 4x slower on the item side, r01f).
+        if os.environ.get("EALS_PEER_PRED_CACHE", "1") == "1" and self._pred_cache_everywhere():
             shared += [_lib.BUF_PC_USER, _lib.BUF_PC_ITEM]
         self.peer_pred_cache = len(shared) == 4
         for which in shared:
