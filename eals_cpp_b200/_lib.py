@@ -50,6 +50,7 @@ SIGNATURES = {
     "eals_init_factors": (C.c_int, [_P]),
     "eals_set_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
     "eals_get_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "eals_get_factor_row": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "eals_set_item_weights": (C.c_int, [_P, C.c_int32, _P]),
     "eals_get_item_weights": (C.c_int, [_P, C.c_int32, _P]),
     "eals_refresh_S": (C.c_int, [_P]),

@@ -1422,6 +1422,18 @@ int eals_get_factors(eals_model* m, int32_t space, double* U, double* V) {
   return EALS_OK;
 }
 
+int eals_get_factor_row(eals_model* m, int32_t which, int32_t row, double* out) {
+  if (!m || !out) return fail(EALS_ERR_ARG, "null argument");
+  if (which != EALS_BUF_U && which != EALS_BUF_V) return fail(EALS_ERR_ARG, "which must be EALS_BUF_U or EALS_BUF_V");
+  const int n = which == EALS_BUF_U ? m->M : m->N;
+  if (row < 0 || row >= n) return fail(EALS_ERR_ARG, "row %d out of range", row);
+  CU(cudaSetDevice(m->p.device));
+  const double* src = (which == EALS_BUF_U ? m->U : m->V) + (size_t)row * m->LD;
+  CU(cudaMemcpyAsync(out, src, sizeof(double) * m->K, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return EALS_OK;
+}
+
 int eals_set_item_weights(eals_model* m, int32_t space, const double* Wi) {
   if (!m || !Wi) return fail(EALS_ERR_ARG, "null argument");
   CU(cudaSetDevice(m->p.device));

@@ -11,7 +11,9 @@
 //   4. build the model, run maxIter iterations, evaluate (main.cpp:227-231).
 // Unlike the reference it takes real arguments:
 //   eals_main [--data yelp.rating] [--factors 64] [--iters 20] [--w0 10] [--alpha 0.75] [--reg 0.01]
-//             [--topk 10] [--no-loss] [--exact-eval] [--device 0]
+//             [--topk 10] [--no-loss] [--exact-eval] [--device 0] [--online U,I]
+// --online U,I: after training and evaluation, add the interaction (U, I) with the online update
+// (updateModel, MF_fastALS.cpp:223-242) and print the prediction before and after.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +38,7 @@ int main(int argc, char** argv) {
   double w0 = 10, reg = 0.01, alpha = 0.75, init_mean = 0, init_stdev = 0.01;
   int factors = 64, maxIter = 20, topK = 10, threadNum = 1, device = 0;
   bool showProgress = false, showLoss = true, exact = false;
+  int online_u = -1, online_i = -1;
   for (int a = 1; a < argc; a++) {
     auto is = [&](const char* f) { return std::strcmp(argv[a], f) == 0; };
     auto next = [&]() -> const char* { if (a + 1 >= argc) { std::fprintf(stderr, "missing value after %s\n", argv[a]); std::exit(2); } return argv[++a]; };
@@ -49,6 +52,7 @@ int main(int argc, char** argv) {
     else if (is("--device")) device = std::atoi(next());
     else if (is("--no-loss")) showLoss = false;
     else if (is("--exact-eval")) exact = true;
+    else if (is("--online")) { if (std::sscanf(next(), "%d,%d", &online_u, &online_i) != 2) { std::fprintf(stderr, "--online wants U,I\n"); return 2; } }
     else { std::fprintf(stderr, "unknown argument %s\n", argv[a]); return 2; }
   }
 
@@ -105,6 +109,13 @@ int main(int argc, char** argv) {
     fals.buildModel();
     std::vector<double> res = fals.evaluate(exact);
     std::cout << "<hr, ndcg, prec>: \t" << res[0] << "\t" << res[1] << "\t" << res[2] << std::endl;
+    if (online_u >= 0) {
+      const double before = fals.predict(online_u, online_i);
+      fals.updateModel(online_u, online_i);
+      std::cout.precision(17);
+      std::cout << "online (" << online_u << "," << online_i << "): predict " << before << " -> "
+                << fals.predict(online_u, online_i) << " loss:" << fals.loss() << std::endl;
+    }
   } catch (const std::exception& e) {
     std::fprintf(stderr, "eals_main: %s\n", e.what());
     return 1;

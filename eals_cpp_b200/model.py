@@ -372,6 +372,56 @@ class MF_fastALS:
         o, n = np.ascontiguousarray(oldVector, np.float64), np.ascontiguousarray(vget, np.float64)
         check(self.lib.eals_patch_SV(self.h, int(i), _ptr(o), _ptr(n)))
 
+    def _factor_row(self, which, r):
+        """One row of U or V as a host vector (U.matrix[u] / V.matrix[i] of the reference)."""
+        out = np.empty(self.factors)
+        check(self.lib.eals_get_factor_row(self.h, which, int(r), _ptr(out)))
+        return out
+
+    def updateModel(self, u, i, patch_S=True, maxIterOnline=10):
+        """Online update (MF_fastALS.cpp:223-242): add the interaction (u, i) with rating 1 = ``w_new``,
+        give a brand-new item the weight w0 / itemCount (and its term in SV), then run 10 alternating
+        single-row updates of user u and item i.
+
+        The reference's version appends past the capacity of its SparseVec arrays and leaves SU / SV
+        stale between the single-row updates; here the matrix is rebuilt with the entry
+        at its sorted position and, with ``patch_S`` (default), the S caches follow every row update
+        (update_user_SU / update_item_SV, MF_fastALS.cpp:324-335, 409-422) as in the paper's incremental
+        mode.  ``patch_S=False`` reproduces the reference's arithmetic (stale caches)."""
+        if self.world > 1:
+            raise NotImplementedError("updateModel drives single rows; use a single-GPU model")
+        u, i = int(u), int(i)
+        if not (0 <= u < self.userCount and 0 <= i < self.itemCount):
+            raise IndexError("updateModel: (u, i) outside the matrix")
+        sm = self.trainMatrix
+        host = lambda a: None if a is None else (a if isinstance(a, np.ndarray) else a.cpu().numpy())
+        rp, ci, cp, ri = host(sm.row_ptr), host(sm.col_idx), host(sm.col_ptr), host(sm.row_idx)
+        rv, cv = host(sm.row_val), host(sm.col_val)
+        a, b = int(rp[u]), int(rp[u + 1])
+        k = a + int(np.searchsorted(ci[a:b], i))
+        if not (k < b and ci[k] == i):                     # trainMatrix.setValue(u, i, 1); W.setValue(u, i, w_new)
+            a2, b2 = int(cp[i]), int(cp[i + 1])
+            k2 = a2 + int(np.searchsorted(ri[a2:b2], u))
+            ci = np.insert(ci, k, np.int32(i)); ri = np.insert(ri, k2, np.int32(u))
+            rp = rp.copy(); rp[u + 1:] += 1
+            cp = cp.copy(); cp[i + 1:] += 1
+            if rv is not None:
+                rv = np.insert(rv, k, 1.0); cv = np.insert(cv, k2, 1.0)
+            self.setTrain(SparseMat(sm.M, sm.N, rp, ci, cp, ri, rv, cv))
+        Wi = self.Wi
+        if Wi[i] == 0.0:                                    # a new item: weight and its term in the SV cache
+            Wi[i] = self.w0 / self.itemCount
+            self.Wi = Wi                                    # uploads and rebuilds SV with the new weight
+        for _ in range(int(maxIterOnline)):
+            old = self._factor_row(_lib.BUF_U, u) if patch_S else None
+            self.update_user_thread(u)
+            if patch_S:
+                self.update_user_SU(old, self._factor_row(_lib.BUF_U, u))
+            old = self._factor_row(_lib.BUF_V, i) if patch_S else None
+            self.update_item_thread(i)
+            if patch_S:
+                self.update_item_SV(i, old, self._factor_row(_lib.BUF_V, i))
+
     def runOneIteration(self):
         """One correct epoch (the reference's version leaves the S caches stale: :163-173)."""
         self.update_user()

@@ -23,6 +23,7 @@
 #ifndef EALS_B200_MF_FASTALS_H
 #define EALS_B200_MF_FASTALS_H
 
+#include <algorithm>
 #include <chrono>
 #include <cfloat>
 #include <cmath>
@@ -65,7 +66,8 @@ class MF_fastALS_T {
     p.n_users = userCount; p.n_items = itemCount; p.factors = factors; p.topk = topK;
     p.w0 = w0; p.alpha = alpha; p.reg = reg; p.init_mean = init_mean; p.init_stdev = init_stdev;
     p.device = device; p.input_space = EALS_HOST;
-    Flat f = flatten(trainMatrix);
+    mat_ = flatten(trainMatrix);
+    const Flat& f = mat_;
     check(eals_create(&p, f.row_ptr.data(), f.col_idx.data(), f.rv(), f.col_ptr.data(),
                       f.row_idx.data(), f.cv(), &h_), "eals_create");
     check(eals_init_factors(h_), "eals_init_factors");   // U.init, V.init, initS (MF_fastALS.cpp:85-90)
@@ -75,9 +77,8 @@ class MF_fastALS_T {
   MF_fastALS_T& operator=(const MF_fastALS_T&) = delete;
 
   void setTrain(const SparseMatT& trainMatrix) {   // MF_fastALS.cpp:94-104
-    Flat f = flatten(trainMatrix);
-    check(eals_set_train(h_, EALS_HOST, f.row_ptr.data(), f.col_idx.data(), f.rv(),
-                         f.col_ptr.data(), f.row_idx.data(), f.cv()), "eals_set_train");
+    mat_ = flatten(trainMatrix);
+    upload_matrix();
   }
   // MF_fastALS.cpp:106-110, working: dense row-major [userCount][factors] / [itemCount][factors].
   void setUV(const double* U, const double* V) { check(eals_set_factors(h_, EALS_HOST, U, V), "eals_set_factors"); }
@@ -144,6 +145,38 @@ class MF_fastALS_T {
     return s;
   }
 
+  // Online update (MF_fastALS.cpp:223-242): add interaction (u, i) with rating 1 (= w_new), give a
+  // brand-new item the weight w0 / itemCount (SV follows), then 10 alternating single-row updates.
+  // The reference appends past the capacity of its SparseVec arrays and leaves SU / SV stale between
+  // the row updates; here the entry goes to its sorted position and, with patch_S
+  // (default), the S caches follow every row update as update_user_SU / update_item_SV intend.
+  // patch_S = false reproduces the reference's arithmetic (stale caches).
+  void updateModel(int u, int i, bool patch_S = true, int maxIterOnline = 10) {
+    if (u < 0 || u >= userCount || i < 0 || i >= itemCount) throw std::out_of_range("updateModel: (u, i) outside the matrix");
+    if (insert_entry(u, i)) upload_matrix();
+    std::vector<double> Wi((size_t)itemCount);
+    check(eals_get_item_weights(h_, EALS_HOST, Wi.data()), "eals_get_item_weights");
+    if (Wi[(size_t)i] == 0.0) {   // a new item
+      Wi[(size_t)i] = w0 / itemCount;
+      check(eals_set_item_weights(h_, EALS_HOST, Wi.data()), "eals_set_item_weights");   // rebuilds SV too
+    }
+    std::vector<double> before((size_t)factors), after((size_t)factors);
+    for (int it = 0; it < maxIterOnline; it++) {
+      if (patch_S) check(eals_get_factor_row(h_, EALS_BUF_U, u, before.data()), "eals_get_factor_row");
+      update_user_thread(u);
+      if (patch_S) {
+        check(eals_get_factor_row(h_, EALS_BUF_U, u, after.data()), "eals_get_factor_row");
+        update_user_SU(before.data(), after.data());
+        check(eals_get_factor_row(h_, EALS_BUF_V, i, before.data()), "eals_get_factor_row");
+      }
+      update_item_thread(i);
+      if (patch_S) {
+        check(eals_get_factor_row(h_, EALS_BUF_V, i, after.data()), "eals_get_factor_row");
+        update_item_SV(i, before.data(), after.data());
+      }
+    }
+  }
+
   void update_user_thread(int u) { check(eals_update_user_row(h_, u), "eals_update_user_row"); }
   void update_item_thread(int i) { check(eals_update_item_row(h_, i), "eals_update_item_row"); }
   void update_user_SU(double* oldVector, double* uget) { check(eals_patch_SU(h_, oldVector, uget), "eals_patch_SU"); }
@@ -199,11 +232,35 @@ class MF_fastALS_T {
       }
     return f;
   }
+  void upload_matrix() {
+    const Flat& f = mat_;
+    check(eals_set_train(h_, EALS_HOST, f.row_ptr.data(), f.col_idx.data(), f.rv(), f.col_ptr.data(),
+                         f.row_idx.data(), f.cv()), "eals_set_train");
+  }
+  // (u, i) with rating 1 into the host copy of the matrix, both orientations, sorted position;
+  // false if it is already there.
+  bool insert_entry(int u, int i) {
+    Flat& f = mat_;
+    auto b = f.col_idx.begin() + f.row_ptr[u], e = f.col_idx.begin() + f.row_ptr[u + 1];
+    auto at = std::lower_bound(b, e, (int32_t)i);
+    if (at != e && *at == i) return false;
+    const size_t k = (size_t)(at - f.col_idx.begin());
+    f.col_idx.insert(f.col_idx.begin() + k, (int32_t)i);
+    f.row_val.insert(f.row_val.begin() + k, 1.0);
+    for (size_t r = (size_t)u + 1; r < f.row_ptr.size(); r++) f.row_ptr[r]++;
+    auto b2 = f.row_idx.begin() + f.col_ptr[i], e2 = f.row_idx.begin() + f.col_ptr[i + 1];
+    const size_t k2 = (size_t)(std::lower_bound(b2, e2, (int32_t)u) - f.row_idx.begin());
+    f.row_idx.insert(f.row_idx.begin() + k2, (int32_t)u);
+    f.col_val.insert(f.col_val.begin() + k2, 1.0);
+    for (size_t c = (size_t)i + 1; c < f.col_ptr.size(); c++) f.col_ptr[c]++;
+    return true;
+  }
   static double seconds_since(std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
 
   eals_model* h_ = nullptr;
+  Flat mat_;   // host copy of the train matrix (CSR + CSC), kept for updateModel
 };
 
 }  // namespace eals_b200

@@ -132,6 +132,10 @@ int eals_init_factors(eals_model* m);
  * given space; either pointer may be NULL to keep that side.  Refreshes the S caches (initS). */
 int eals_set_factors(eals_model* m, int32_t space, const double* U, const double* V);
 int eals_get_factors(eals_model* m, int32_t space, double* U, double* V);
+/* One factor row to the host: out[factors] = U[row] (which = EALS_BUF_U) or V[row] (EALS_BUF_V) —
+ * U.matrix[u] / V.matrix[i] of the reference (MF_fastALS.h:31-32); what update_user_SU /
+ * update_item_SV callers and the online updateModel (MF_fastALS.cpp:223-242) need per step. */
+int eals_get_factor_row(eals_model* m, int32_t which, int32_t row, double* out);
 
 /* Public member Wi (MF_fastALS.h:46). set refreshes SV. */
 int eals_set_item_weights(eals_model* m, int32_t space, const double* Wi);

@@ -1,0 +1,83 @@
+"""The C++ drop-in path end to end on a GPU: eals_main (host/eals_main.cpp over include/MF_fastALS.h
+over the C ABI) reads a ratings file like the reference's main.cpp:73-205, trains, evaluates and runs
+one online update; its printed losses and metrics must match the CPU oracle on the same split."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ratings(path, M=120, N=80, seed=4):
+    """`user item score timestamp` lines, users contiguous from 0, unique timestamps per user (the
+    reference's std::sort is unstable on ties), a few duplicate (u, i) pairs to exercise the dedup."""
+    rng = np.random.default_rng(seed)
+    lines, split = [], []
+    for u in range(M):
+        n = int(rng.integers(3, 25))
+        items = rng.integers(0, N, size=n)
+        ts = rng.permutation(10_000)[:n] + 1
+        for it, t in zip(items, ts):
+            lines.append(f"{u}\t{it}\t{float(rng.integers(1, 6))}\t{t}")
+        order = np.argsort(ts)
+        test_item = int(items[order[-1]])
+        train = sorted(set(int(x) for x in items[order[:-1]]))        # newest -> test, the rest deduplicated
+        split.append((train, test_item))
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return split
+
+
+def test_cpp_driver_trains_evaluates_and_updates_online(tmp_path):
+    from eals_cpp_b200 import build
+    from oracle.bindings import PortModel, csr_to_csc
+    exe = build.build_host_example()
+    data = tmp_path / "tiny.rating"
+    split = _ratings(str(data))
+    M = len(split)
+    N = 1 + max(max(t + [g]) for t, g in split)
+    K, iters = 8, 3
+    res = subprocess.run([exe, "--data", str(data), "--factors", str(K), "--iters", str(iters), "--online", "3,5"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    out = res.stdout
+    assert f"#Users\t{M}" in out and f"#items\t{N}" in out          # main.cpp:212-216 lines
+    losses = [float(x) for x in re.findall(r"Iter=\d+ \S+ [-+] loss:(\S+)", out)]
+    assert len(losses) == iters
+
+    row_ptr = np.concatenate([[0], np.cumsum([len(t) for t, _ in split])]).astype(np.int64)
+    col_idx = np.concatenate([np.array(t, np.int32) for t, _ in split])
+    gt = np.array([g for _, g in split], np.int32)
+    port = PortModel(M, N, row_ptr, col_idx, factors=K)
+    for it in range(iters):
+        port.update_user(); port.SU = port.p.gram_plain(port.U)
+        port.update_item(); port.SV = port.p.gram_weighted(port.V, port.Wi)
+        assert abs(losses[it] - port.loss()) <= 1e-5 * abs(port.loss())   # printed with 6 significant digits
+    hr, ndcg, prec = [float(x) for x in re.search(r"<hr, ndcg, prec>: \t(\S+)\t(\S+)\t(\S+)", out).groups()]
+    want = port.evaluate(gt, 10, compat=True)[0]
+    assert np.allclose([hr, ndcg, prec], want, atol=5e-6)
+
+    # online update of (3, 5): same schedule on the oracle (S caches patched after every row)
+    u, i = 3, 5
+    before = float(port.U[u] @ port.V[i])
+    rows = [list(col_idx[row_ptr[r]:row_ptr[r + 1]]) for r in range(M)]
+    if i not in rows[u]:
+        rows[u] = sorted(rows[u] + [i])
+    port.row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    port.col_idx = np.concatenate([np.array(r, np.int32) for r in rows])
+    port.col_ptr, port.row_idx, port.cval, _ = csr_to_csc(M, N, port.row_ptr, port.col_idx, None)
+    if port.Wi[i] == 0.0:
+        port.Wi[i] = 10.0 / N
+        port.SV = port.p.gram_weighted(port.V, port.Wi)
+    for _ in range(10):   # the oracle's row sweeps patch SU / SV themselves (MF_fastALS.cpp:127-132, 146-152)
+        port.update_user(u, u + 1)
+        port.update_item(i, i + 1)
+    m = re.search(r"online \(3,5\): predict (\S+) -> (\S+) loss:(\S+)", out)
+    got_before, got_after, got_loss = (float(x) for x in m.groups())
+    assert abs(got_before - before) < 1e-10
+    assert abs(got_after - float(port.U[u] @ port.V[i])) < 1e-10
+    assert abs(got_loss - port.loss()) <= 1e-10 * abs(port.loss())

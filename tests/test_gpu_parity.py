@@ -314,6 +314,49 @@ def test_evaluate_matches_oracle_bug_for_bug(scale, first_chunk, monkeypatch):
         assert fals.evaluate_for_user(u, int(gt[u]), topK) == [whr[u], wndcg[u], wprec[u]]
 
 
+@pytest.mark.parametrize("patch_S", [True, False])
+def test_online_update_model(patch_S):
+    """updateModel (MF_fastALS.cpp:223-242): new interaction + 10 alternating single-row updates, with
+    the S caches patched after every row (intended behaviour) or left stale (the reference's arithmetic).
+    Checked against the oracle's single-row sweeps on the matrix with the entry inserted; one case adds
+    the first rating of an item that had none (weight w0 / itemCount, SV rebuilt)."""
+    M, N, K = 300, 200, 16
+    row_ptr, col_idx = random_csr(M, N, 12, seed=9, empty_frac=0.02)
+    # make item 7 unseen so that the "new item" branch runs
+    rows0 = [[c for c in col_idx[row_ptr[r]:row_ptr[r + 1]] if c != 7] for r in range(M)]
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows0])]).astype(np.int64)
+    col_idx = np.array([c for r in rows0 for c in r], np.int32)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    fals.update_user(); port.update_user(); port.SU = port.p.gram_plain(port.U)
+    fals.update_item(); port.update_item(); port.SV = port.p.gram_weighted(port.V, port.Wi)
+    for (u, i) in [(5, 7), (11, 40)]:
+        fals.updateModel(u, i, patch_S=patch_S)
+        # oracle: insert the entry, then the same single-row schedule
+        rows = [list(port.col_idx[port.row_ptr[r]:port.row_ptr[r + 1]]) for r in range(M)]
+        if i not in rows[u]:
+            rows[u] = sorted(rows[u] + [i])
+        rp = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+        ci = np.concatenate([np.array(r, np.int32) for r in rows])
+        from oracle.bindings import csr_to_csc
+        port.row_ptr, port.col_idx = rp, ci
+        port.col_ptr, port.row_idx, port.cval, _ = csr_to_csc(M, N, rp, ci, None)
+        if port.Wi[i] == 0.0:
+            port.Wi[i] = 10.0 / N
+            port.SV = port.p.gram_weighted(port.V, port.Wi)
+        for _ in range(10):   # the oracle's row sweeps patch SU / SV themselves (MF_fastALS.cpp:127-132, 146-152)
+            su, sv = port.SU.copy(), port.SV.copy()
+            port.update_user(u, u + 1)
+            if not patch_S:
+                port.SU[...] = su
+            port.update_item(i, i + 1)
+            if not patch_S:
+                port.SV[...] = sv
+        assert np.abs(fals.U - port.U).max() < 1e-10
+        assert np.abs(fals.V - port.V).max() < 1e-10
+        assert np.abs(fals.SU - port.SU).max() <= 1e-10 * np.abs(port.SU).max()
+        assert np.abs(fals.SV - port.SV).max() <= 1e-10 * np.abs(port.SV).max()
+
+
 def test_errors_are_reported_not_swallowed():
     from eals_cpp_b200._lib import EalsError
     from eals_cpp_b200.model import MF_fastALS, SparseMat
