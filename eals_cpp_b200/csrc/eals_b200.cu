@@ -198,6 +198,12 @@ struct eals_model {
   uint32_t *route_src_u = nullptr, *route_dst_u = nullptr, *route_src_i = nullptr, *route_dst_i = nullptr;
   size_t cap_stage_u = 0, cap_stage_i = 0, cap_rsrc_u = 0, cap_rdst_u = 0, cap_rsrc_i = 0, cap_rdst_i = 0;
   bool routed = false;
+  // multi-rank, host input: device copies of the FULL offset / index arrays for the position maps, and the
+  // sort scratch of the routes — kept across setTrain (cudaMalloc / cudaFree per call cost 0.5 s at c4)
+  int64_t *full_rp = nullptr, *full_cp = nullptr;
+  int32_t *full_ci = nullptr, *full_ri = nullptr;
+  unsigned char* route_tmp = nullptr;
+  size_t cap_full_rp = 0, cap_full_cp = 0, cap_full_ci = 0, cap_full_ri = 0, cap_route_tmp = 0;
   eals::PcOut out_to_items = {}, out_to_users = {};   // where the other side's caches live (all ranks)
   int n_ranks = 1, rank = 0;
   bool pc_attached = false;      // caches usable: single rank, or both peers' cache sets mapped
@@ -315,11 +321,9 @@ int build_routes(eals_model* m, const uint32_t* map, int64_t n, double** stage, 
   OK(check_launch(m));
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, map, *rdst, iota, *rsrc, (int)n, 0, 32, m->stream);
-  void* tmp = nullptr;
-  CU(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
-  const cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, map, *rdst, iota, *rsrc, (int)n, 0, 32, m->stream);
+  OK(dev_reserve(&m->route_tmp, &m->cap_route_tmp, std::max<size_t>(tmp_bytes, 16)));
+  const cudaError_t e = cub::DeviceRadixSort::SortPairs(m->route_tmp, tmp_bytes, map, *rdst, iota, *rsrc, (int)n, 0, 32, m->stream);
   cudaStreamSynchronize(m->stream);
-  cudaFree(tmp);
   if (e != cudaSuccess) return fail(EALS_ERR_CUDA, "route sort -> %s", cudaGetErrorString(e));
   return EALS_OK;
 }
@@ -365,19 +369,18 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   // full arrays of the OTHER orientation on the device (temporary copies when the input is on the host
   // and this model holds only a slice)
   const int64_t* d_rp = nullptr; const int32_t* d_ci = nullptr; const int64_t* d_cp = nullptr; const int32_t* d_ri = nullptr;
-  int64_t *t_rp = nullptr, *t_cp = nullptr; int32_t *t_ci = nullptr, *t_ri = nullptr;
   if (single) {
     d_rp = m->users.ptr; d_ci = m->users.idx; d_cp = m->items.ptr; d_ri = m->items.idx;
   } else if (space == EALS_DEVICE) {
     d_rp = row_ptr; d_ci = col_idx; d_cp = col_ptr; d_ri = row_idx;
   } else {
-    OK(dev_alloc(&t_rp, (size_t)m->M + 1)); OK(dev_alloc(&t_cp, (size_t)m->N + 1));
-    OK(dev_alloc(&t_ci, (size_t)nnz_total)); OK(dev_alloc(&t_ri, (size_t)nnz_total));
-    CU(cudaMemcpyAsync(t_rp, row_ptr, sizeof(int64_t) * (m->M + 1), cudaMemcpyHostToDevice, m->stream));
-    CU(cudaMemcpyAsync(t_cp, col_ptr, sizeof(int64_t) * (m->N + 1), cudaMemcpyHostToDevice, m->stream));
-    CU(cudaMemcpyAsync(t_ci, col_idx, sizeof(int32_t) * nnz_total, cudaMemcpyHostToDevice, m->stream));
-    CU(cudaMemcpyAsync(t_ri, row_idx, sizeof(int32_t) * nnz_total, cudaMemcpyHostToDevice, m->stream));
-    d_rp = t_rp; d_ci = t_ci; d_cp = t_cp; d_ri = t_ri;
+    OK(dev_reserve(&m->full_rp, &m->cap_full_rp, (size_t)m->M + 1)); OK(dev_reserve(&m->full_cp, &m->cap_full_cp, (size_t)m->N + 1));
+    OK(dev_reserve(&m->full_ci, &m->cap_full_ci, (size_t)nnz_total)); OK(dev_reserve(&m->full_ri, &m->cap_full_ri, (size_t)nnz_total));
+    CU(cudaMemcpyAsync(m->full_rp, row_ptr, sizeof(int64_t) * (m->M + 1), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(m->full_cp, col_ptr, sizeof(int64_t) * (m->N + 1), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(m->full_ci, col_idx, sizeof(int32_t) * nnz_total, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(m->full_ri, row_idx, sizeof(int32_t) * nnz_total, cudaMemcpyHostToDevice, m->stream));
+    d_rp = m->full_rp; d_ci = m->full_ci; d_cp = m->full_cp; d_ri = m->full_ri;
   }
   const int64_t nu = m->users.nnz, ni = m->items.nnz;
   OK(dev_reserve(&m->pc_u, &m->cap_pc_u, (size_t)nu));
@@ -398,7 +401,6 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   int h_bad = 0;
   CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
-  if (t_rp) { cudaFree(t_rp); cudaFree(t_cp); cudaFree(t_ci); cudaFree(t_ri); }
   if (h_bad) return fail(EALS_ERR_ARG, "the CSR and CSC arrays do not describe the same matrix");
   // destination tables; the own rank's entries are filled now, the peers' by eals_ipc_attach
   const int nr = single ? 1 : m->n_ranks, me = single ? 0 : m->rank;
@@ -1281,6 +1283,7 @@ int eals_destroy(eals_model* m) {
   cudaFree(m->pc_u); cudaFree(m->pc_i); cudaFree(m->map_u); cudaFree(m->map_i);
   cudaFree(m->pc_stage_u); cudaFree(m->pc_stage_i);
   cudaFree(m->route_src_u); cudaFree(m->route_dst_u); cudaFree(m->route_src_i); cudaFree(m->route_dst_i);
+  cudaFree(m->full_rp); cudaFree(m->full_cp); cudaFree(m->full_ci); cudaFree(m->full_ri); cudaFree(m->route_tmp);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
