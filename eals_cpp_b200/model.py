@@ -206,30 +206,36 @@ class MF_fastALS:
             check(self.lib.eals_init_factors(self.h))     # MF_fastALS.cpp:85-90
 
     # ---- helpers ---------------------------------------------------------------------------------
-    def _attach_peers(self):
-        """Exchange the CUDA IPC handles of the U and V replicas and map the other ranks' buffers, so
-        that the sweep kernels store finished rows into every replica themselves (the all-gather of
-        SURVEY.md §8e fused into the sweep).  Needs all ranks on one box with peer access."""
+    def _attach_peers(self, factors=True):
+        """Exchange CUDA IPC handles and map the other ranks' buffers: the U and V replicas (the sweep
+        kernels then store finished rows into every replica themselves — the all-gather of SURVEY.md §8e
+        fused into the sweep) and the prediction caches.  Needs all ranks on one box with peer access.
+        ``factors=False`` (after setTrain): only the prediction caches, the replicas never move."""
         import torch
         import torch.distributed as dist
         if self.world - 1 > 7:
             return
         dev = f"cuda:{self.device}"
-        shared = [_lib.BUF_U, _lib.BUF_V]
+        shared = [_lib.BUF_U, _lib.BUF_V] if factors else []
         # The prediction caches are shared across ranks too: a sweep stages its final predictions locally
         # and a second kernel routes them to their owners in destination order (EALS_PC_ROUTE=0: scattered
         # 8-byte peer stores straight from the sweep kernels, measured 4x slower on the item side, r01f).
-        if os.environ.get("EALS_PEER_PRED_CACHE", "1") == "1" and self._pred_cache_everywhere():
+        pc = os.environ.get("EALS_PEER_PRED_CACHE", "1") == "1" and self._pred_cache_everywhere()
+        if pc:
             shared += [_lib.BUF_PC_USER, _lib.BUF_PC_ITEM]
-        self.peer_pred_cache = len(shared) == 4
-        for which in shared:
-            mine = np.zeros(64, np.uint8)
-            check(self.lib.eals_ipc_handle(self.h, which, _ptr(mine)))
-            t = torch.from_numpy(mine).to(dev)
-            allh = [torch.empty_like(t) for _ in range(self.world)]
-            dist.all_gather(allh, t, group=self.group)
-            others = np.concatenate([allh[r].cpu().numpy() for r in range(self.world) if r != self.rank])
-            others = np.ascontiguousarray(others, np.uint8)
+        self.peer_pred_cache = pc
+        if not shared:
+            return
+        # one all-gather for all handles
+        mine = np.zeros((len(shared), 64), np.uint8)
+        for k, which in enumerate(shared):
+            check(self.lib.eals_ipc_handle(self.h, which, _ptr(mine[k])))
+        t = torch.from_numpy(mine).to(dev)
+        allh = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t, group=self.group)
+        allh = [a.cpu().numpy() for a in allh]
+        for k, which in enumerate(shared):
+            others = np.ascontiguousarray(np.concatenate([allh[r][k] for r in range(self.world) if r != self.rank]), np.uint8)
             check(self.lib.eals_ipc_attach(self.h, which, self.world - 1, _ptr(others)))
         self.peer_store = True
 
@@ -333,11 +339,17 @@ class MF_fastALS:
     def setTrain(self, trainMatrix: SparseMat):
         sm = trainMatrix
         space = _lib.EALS_DEVICE if sm.on_device else _lib.EALS_HOST
+        import time as _t
+        t0 = _t.perf_counter()
         check(self.lib.eals_set_train(self.h, space, _ptr(sm.row_ptr), _ptr(sm.col_idx), _ptr(sm.row_val),
                                       _ptr(sm.col_ptr), _ptr(sm.row_idx), _ptr(sm.col_val)))
         self.trainMatrix = sm
+        t1 = _t.perf_counter()
         if self.peer_store:                               # the prediction caches were rebuilt: share them again
-            self._attach_peers()
+            self._attach_peers(factors=False)
+        if os.environ.get("EALS_VERBOSE") == "1":
+            print(f"[eals] rank {self.rank} setTrain: library {1e3 * (t1 - t0):.1f} ms, attach {1e3 * (_t.perf_counter() - t1):.1f} ms",
+                  file=sys.stderr)
 
     # ---- half-epochs ---------------------------------------------------------------------------------
     def update_user(self):
