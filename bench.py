@@ -358,7 +358,8 @@ def main():
         for it in range(1 + args.e2e_steps):
             barrier()
             t0 = time.perf_counter()
-            fals.setTrain(sm_host)          # H2D of the CSR + CSC slices, bucketing
+            fals.setTrain(sm_host)          # H2D of the CSR + CSC arrays, bucketing, position maps
+            h2d = getattr(fals, "_h2d_bytes_last", h2d)   # several ranks: 1/world chunk each + all-gather
             torch.cuda.synchronize(); t1 = time.perf_counter()
             epoch()
             torch.cuda.synchronize(); t2 = time.perf_counter()

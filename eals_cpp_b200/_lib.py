@@ -78,6 +78,8 @@ SIGNATURES = {
     "eals_ipc_handle": (C.c_int, [_P, C.c_int32, _P]),
     "eals_ipc_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "eals_ipc_detach": (C.c_int, [_P]),
+    "eals_ipc_generation": (C.c_int, [_P]),
+    "eals_ipc_gc": (C.c_int, [_P]),
     "eals_nnz": (C.c_int64, [_P]),
     "eals_kernel_launches": (C.c_int64, [_P]),
     "eals_timings": (C.c_int, [_P, _P]),

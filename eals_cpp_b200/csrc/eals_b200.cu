@@ -198,6 +198,10 @@ struct eals_model {
   uint32_t *route_src_u = nullptr, *route_dst_u = nullptr, *route_src_i = nullptr, *route_dst_i = nullptr;
   size_t cap_stage_u = 0, cap_stage_i = 0, cap_rsrc_u = 0, cap_rdst_u = 0, cap_rsrc_i = 0, cap_rdst_i = 0;
   bool routed = false;
+  // multi-rank: a prediction cache that had to grow is not freed while peers may still map it (CUDA IPC):
+  // the old buffer waits here until eals_ipc_gc; ipc_gen counts such reallocations
+  std::vector<void*> graveyard;
+  int ipc_gen = 0;
   // multi-rank, host input: device copies of the FULL offset / index arrays for the position maps, and the
   // sort scratch of the routes — kept across setTrain (cudaMalloc / cudaFree per call cost 0.5 s at c4)
   int64_t *full_rp = nullptr, *full_cp = nullptr;
@@ -342,11 +346,7 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   StageTimer tm;
   m->pc_u_valid = m->pc_i_valid = false;
   m->pcache_on = false;
-  if (m->n_ranks > 1) {   // the peers' mappings belong to the previous matrix
-    CU(cudaStreamSynchronize(m->stream));
-    close_pc_peers(m, m->out_to_users, m->pc_users_attached);
-    close_pc_peers(m, m->out_to_items, m->pc_items_attached);
-  }
+  const bool was_attached = m->pc_attached;
   m->pc_attached = false;
   const bool single = m->ub == 0 && m->ue == m->M && m->ib == 0 && m->ie == m->N;
   const bool multi = !single && m->n_ranks > 1;
@@ -383,8 +383,16 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
     d_rp = m->full_rp; d_ci = m->full_ci; d_cp = m->full_cp; d_ri = m->full_ri;
   }
   const int64_t nu = m->users.nnz, ni = m->items.nnz;
-  OK(dev_reserve(&m->pc_u, &m->cap_pc_u, (size_t)nu));
-  OK(dev_reserve(&m->pc_i, &m->cap_pc_i, (size_t)ni));
+  {   // the caches themselves: growing one while peers map it (multi-rank) must not free it under them
+    auto reserve_shared = [&](double** p, size_t* cap, size_t n) -> int {
+      if (*p && n <= *cap) return EALS_OK;
+      if (*p && m->n_ranks > 1) { m->graveyard.push_back(*p); *p = nullptr; *cap = 0; }
+      m->ipc_gen++;
+      return dev_reserve(p, cap, n + n / 16);   // a little headroom: matrices of similar size keep the buffers
+    };
+    OK(reserve_shared(&m->pc_u, &m->cap_pc_u, (size_t)nu));
+    OK(reserve_shared(&m->pc_i, &m->cap_pc_i, (size_t)ni));
+  }
   OK(dev_reserve(&m->map_u, &m->cap_map_u, (size_t)nu));
   OK(dev_reserve(&m->map_i, &m->cap_map_i, (size_t)ni));
   int* bad = m->flags + 2;
@@ -404,7 +412,12 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   if (h_bad) return fail(EALS_ERR_ARG, "the CSR and CSC arrays do not describe the same matrix");
   // destination tables; the own rank's entries are filled now, the peers' by eals_ipc_attach
   const int nr = single ? 1 : m->n_ranks, me = single ? 0 : m->rank;
-  m->out_to_items = eals::PcOut{}; m->out_to_users = eals::PcOut{};
+  {   // the peers' mappings stay (their buffers only move when THEY report a new ipc generation)
+    const eals::PcOut old_items = m->out_to_items, old_users = m->out_to_users;
+    m->out_to_items = eals::PcOut{}; m->out_to_users = eals::PcOut{};
+    if (multi && was_attached)
+      for (int r = 0; r < nr; r++) { m->out_to_items.base[r] = old_items.base[r]; m->out_to_users.base[r] = old_users.base[r]; }
+  }
   m->out_to_items.n = m->out_to_users.n = nr;
   for (int r = 0; r <= nr; r++) {
     m->out_to_items.bound[r] = (uint32_t)cp[r];   // user sweeps write CSC-ordered caches
@@ -412,7 +425,7 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   }
   m->out_to_items.base[me] = m->pc_i;
   m->out_to_users.base[me] = m->pc_u;
-  m->pc_attached = single;
+  m->pc_attached = single || (multi && was_attached);
   tm.lap("pred cache: position maps");
   m->routed = false;
   if (multi && !(getenv("EALS_PC_ROUTE") && getenv("EALS_PC_ROUTE")[0] == '0')) {
@@ -1283,6 +1296,7 @@ int eals_destroy(eals_model* m) {
   cudaFree(m->pc_u); cudaFree(m->pc_i); cudaFree(m->map_u); cudaFree(m->map_i);
   cudaFree(m->pc_stage_u); cudaFree(m->pc_stage_i);
   cudaFree(m->route_src_u); cudaFree(m->route_dst_u); cudaFree(m->route_src_i); cudaFree(m->route_dst_i);
+  for (void* p : m->graveyard) cudaFree(p);
   cudaFree(m->full_rp); cudaFree(m->full_cp); cudaFree(m->full_ci); cudaFree(m->full_ri); cudaFree(m->route_tmp);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
@@ -1649,6 +1663,17 @@ int eals_ipc_handle(eals_model* m, int32_t which, void* handle_out) {
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, buf));
   std::memcpy(handle_out, &h, sizeof(h));
+  return EALS_OK;
+}
+
+int eals_ipc_generation(eals_model* m) { return m ? m->ipc_gen : -1; }
+
+int eals_ipc_gc(eals_model* m) {
+  if (!m) return EALS_OK;
+  cudaSetDevice(m->p.device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (void* p : m->graveyard) cudaFree(p);
+  m->graveyard.clear();
   return EALS_OK;
 }
 

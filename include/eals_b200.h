@@ -211,6 +211,12 @@ int eals_sync(eals_model* m);
 int eals_ipc_handle(eals_model* m, int32_t which, void* handle_out);
 int eals_ipc_attach(eals_model* m, int32_t which, int32_t n_peers, const void* handles);
 int eals_ipc_detach(eals_model* m);
+/* A prediction cache that has to grow in eals_set_train is not freed while peers may still map it:
+ * eals_ipc_generation changes when that happened on this rank (then ALL ranks exchange handles and attach
+ * again), eals_ipc_gc frees the retired buffers once every peer has re-attached.  With unchanged
+ * generations on all ranks the existing mappings stay valid and no handle exchange is needed. */
+int eals_ipc_generation(eals_model* m);
+int eals_ipc_gc(eals_model* m);
 int64_t eals_nnz(const eals_model* m);                     /* nonzeros of the owned user rows     */
 int64_t eals_kernel_launches(const eals_model* m);         /* kernels launched so far             */
 /* Device milliseconds of the most recent call of each kind: [0] user sweep, [1] user Gram,

@@ -40,6 +40,27 @@ def main():
         fals.update_item(); port.update_item()
         lg, lc = fals.loss(), port.loss()
         assert abs(lg - lc) <= 1e-10 * abs(lc), (rank, it, lg, lc)
+    # setTrain on several ranks (chunked upload + all-gather of the index arrays, caches rebuilt and
+    # re-shared), then one more epoch
+    fals.setTrain(sm)
+    fals.update_user(); port.update_user()
+    fals.update_item(); port.update_item()
+    lg, lc = fals.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc), (rank, "after setTrain", lg, lc)
+    # a LARGER matrix: the prediction caches have to grow, so the ranks exchange IPC handles again
+    from oracle.bindings import csr_to_csc
+    for u in rng.choice(M, size=900, replace=False):
+        rows[u].update(int(c) for c in rng.choice(N, size=12, replace=False))
+    row_ptr2 = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col_idx2 = np.concatenate([np.array(sorted(r), np.int32) for r in rows])
+    fals.setTrain(SparseMat.from_csr(M, N, row_ptr2, col_idx2))
+    port.row_ptr, port.col_idx = row_ptr2, col_idx2
+    port.col_ptr, port.row_idx, port.cval, _ = csr_to_csc(M, N, row_ptr2, col_idx2, None)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+    lg, lc = fals.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc), (rank, "after growing setTrain", lg, lc)
     assert np.abs(fals.U - port.U).max() < 1e-10, rank        # every replica is complete
     assert np.abs(fals.V - port.V).max() < 1e-10, rank
     assert np.abs(fals.SU - port.SU).max() <= 1e-11 * np.abs(port.SU).max()
