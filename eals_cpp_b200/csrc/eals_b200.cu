@@ -140,6 +140,8 @@ struct Side {
   int slab = eals::kMaxSlab;                // nonzeros per slab (= threads of a heavy_step CTA)
   int32_t *hrow_id = nullptr, *hrow_unit0 = nullptr, *hrow_units = nullptr;
   int32_t *hrow_grp0 = nullptr, *hrow_grps = nullptr, *grp_unit0 = nullptr, *grp_cnt = nullptr;
+  int64_t* hrow_poff = nullptr;       // offset of heavy row h in the compact prediction cache
+  size_t cap_hrow_poff = 0;
   int32_t* unit_launch = nullptr;     // scratch: sorted canonical unit ids of a batch
   uint32_t *sort_keys = nullptr, *sort_keys_out = nullptr;   // scratch of build_launch_order, kept across setTrain
   int32_t* sort_vals = nullptr;
@@ -241,6 +243,7 @@ void free_side(Side& s) {
   cudaFree(s.pred); cudaFree(s.delta);
   cudaFree(s.units_canon); cudaFree(s.units_launch);
   cudaFree(s.hrow_id); cudaFree(s.hrow_unit0); cudaFree(s.hrow_units);
+  cudaFree(s.hrow_poff);
   cudaFree(s.hrow_grp0); cudaFree(s.hrow_grps); cudaFree(s.grp_unit0); cudaFree(s.grp_cnt); cudaFree(s.unit_launch);
   cudaFree(s.sort_keys); cudaFree(s.sort_keys_out); cudaFree(s.sort_vals); cudaFree(s.sort_tmp);
   s = Side();
@@ -256,19 +259,33 @@ int copy_in(T* dst, const T* src, size_t n, int space, cudaStream_t st) {
 }
 
 // One warp per row (grid-stride): every index in range and strictly larger than its predecessor.
-__global__ void check_sorted_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                    int rows, int limit, int* __restrict__ bad) {
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  bool ok = true;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
-    const int64_t p0 = ptr[r], p1 = ptr[r + 1];
-    for (int64_t p = p0 + lane; p < p1; p += 32) {
-      const int c = idx[p];
-      ok &= c >= 0 && c < limit && (p == p0 || idx[p - 1] < c);
-    }
+// Indices in range and strictly ascending inside every row, flat over the nonzeros so that a column with
+// millions of entries costs no more than its share (one warp per row took 26 ms on c4's item side):
+// `descents` counts the positions whose index does not exceed its predecessor's; each of them is legal
+// only as the first nonzero of a row, which check_row_starts_kernel counts — equal counts <=> sorted.
+__global__ void check_indices_kernel(const int32_t* __restrict__ idx, int64_t nnz, int limit,
+                                     int* __restrict__ bad, unsigned long long* __restrict__ descents) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool oob = false, desc = false;
+  if (q < nnz) {
+    const int c = idx[q];
+    oob = c < 0 || c >= limit;
+    desc = q > 0 && idx[q - 1] >= c;
   }
-  if (!ok) atomicExch(bad, 1);
+  if (__syncthreads_or(oob) && threadIdx.x == 0) atomicExch(bad, 1);
+  const int nd = __syncthreads_count(desc);
+  if (nd && threadIdx.x == 0) atomicAdd(descents, (unsigned long long)nd);
+}
+__global__ void check_row_starts_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int rows,
+                                        unsigned long long* __restrict__ starts) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false;
+  if (r < rows) {
+    const int64_t q = ptr[r];
+    hit = q > 0 && ptr[r + 1] > q && idx[q - 1] >= idx[q];
+  }
+  const int n = __syncthreads_count(hit);
+  if (n && threadIdx.x == 0) atomicAdd(starts, (unsigned long long)n);
 }
 
 int ensure_partials(eals_model* m, size_t n);
@@ -395,7 +412,7 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   }
   OK(dev_reserve(&m->map_u, &m->cap_map_u, (size_t)nu));
   OK(dev_reserve(&m->map_i, &m->cap_map_i, (size_t)ni));
-  int* bad = m->flags + 2;
+  int* bad = m->flags + 14;
   CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
   CU(cudaMemsetAsync(m->map_u, 0xff, sizeof(uint32_t) * (size_t)nu, m->stream));   // unreached CSR entries stay invalid
   {
@@ -437,6 +454,27 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   m->pcache_on = true;
   if (const char* e = getenv("EALS_PRED_REFRESH_EVERY")) m->pred_refresh_every = atoi(e);
   return EALS_OK;
+}
+
+// Slab descriptors in canonical order, one thread per slab (the host only keeps per-ROW tables).
+__global__ void unit_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ hrow_id,
+                                 const int32_t* __restrict__ hrow_unit0, const int64_t* __restrict__ hrow_poff,
+                                 int n_hrows, int n_units, int slab, eals::UnitDesc* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  int lo = 0, hi = n_hrows;                 // largest h with hrow_unit0[h] <= u
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (hrow_unit0[mid] <= u) lo = mid; else hi = mid;
+  }
+  const int h = lo, r = hrow_id[h];
+  const int64_t k = (int64_t)(u - hrow_unit0[h]) * slab;
+  const int64_t p0 = ptr[r], n = ptr[r + 1] - p0;
+  eals::UnitDesc d;
+  d.off = p0 + k; d.poff = hrow_poff[h] + k;
+  d.cnt = (int)(n - k < slab ? n - k : slab);
+  d.row = r; d.hrow = h; d.slot = u;
+  out[u] = d;
 }
 
 __global__ void unit_key_kernel(const int32_t* __restrict__ idx, const eals::UnitDesc* __restrict__ canon, int u0, int n,
@@ -534,9 +572,14 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
   // indices must ascend strictly inside a row and stay in range (main.cpp:198-205 order)
   int* sorted_flag = nullptr;
   if (s.rows > 0) {
-    int* bad = m->flags + (&s == &m->users ? 0 : 1);
-    CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
-    check_sorted_kernel<<<std::min((s.rows + 7) / 8, 64 * m->sm_count), 256, 0, m->stream>>>(s.ptr, s.idx, s.rows, other_dim, bad);
+    int* bad = m->flags + (&s == &m->users ? 0 : 8);          // 6 ints: bad, pad, descents (u64), row-start descents (u64)
+    unsigned long long* counts = reinterpret_cast<unsigned long long*>(bad + 2);
+    CU(cudaMemsetAsync(bad, 0, 6 * sizeof(int), m->stream));
+    if (s.nnz > 0) {
+      check_indices_kernel<<<(unsigned)((s.nnz + 255) / 256), 256, 0, m->stream>>>(s.idx, s.nnz, other_dim, bad, counts);
+      OK(check_launch(m));
+    }
+    check_row_starts_kernel<<<(s.rows + 255) / 256, 256, 0, m->stream>>>(s.ptr, s.idx, s.rows, counts + 1);
     OK(check_launch(m));
     sorted_flag = bad;   // read back after the host-side bucketing below (overlaps the upload)
   }
@@ -597,10 +640,13 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
   CU(cudaMemcpyAsync(s.order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, m->stream));
 
   if (sorted_flag) {
-    int h_bad = 0;
-    CU(cudaMemcpyAsync(&h_bad, sorted_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    int h_flags[6] = {0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(h_flags, sorted_flag, sizeof(h_flags), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
-    if (h_bad) return fail(EALS_ERR_ARG, "indices inside a row must be strictly ascending and in range");
+    unsigned long long h_counts[2];
+    std::memcpy(h_counts, h_flags + 2, sizeof(h_counts));
+    if (h_flags[0] || h_counts[0] != h_counts[1])
+      return fail(EALS_ERR_ARG, "indices inside a row must be strictly ascending and in range");
   }
   tm.lap("side: bucket rows + validate");
   // heavy rows -> slabs ("units") of kSlab nonzeros and batches of rows
@@ -608,7 +654,8 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     const int hb = s.first[kHeavyBucket], he = s.first[kHeavyBucket + 1];
     s.n_hrows = he - hb;
     std::vector<int32_t> hrow_id, grp_unit0, grp_cnt;
-    std::vector<eals::UnitDesc> units;
+    std::vector<int64_t> hrow_poff;
+    int64_t n_units_total = 0;
     // EALS_SLAB=128|256: nonzeros per slab = threads per heavy_step CTA
     s.slab = (getenv("EALS_SLAB") && atoi(getenv("EALS_SLAB")) == 256) ? 256 : 128;
     s.h_hrow_unit0.clear(); s.h_hrow_units.clear(); s.batches.clear(); s.h_row_to_hrow.clear();
@@ -616,8 +663,8 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
     {
       int64_t hn = 0;
       for (int h = 0; h < s.n_hrows; h++) { const int r = order[hb + h]; hn += s.h_ptr[r + 1] - s.h_ptr[r]; }
-      const size_t est = (size_t)(hn / s.slab) + (size_t)s.n_hrows + 1;
-      units.reserve(est);
+      (void)hn;
+      hrow_poff.reserve((size_t)s.n_hrows);
       hrow_id.reserve((size_t)s.n_hrows); s.h_hrow_unit0.reserve((size_t)s.n_hrows); s.h_hrow_units.reserve((size_t)s.n_hrows);
     }
     int64_t poff = 0, batch_nnz = 0;
@@ -629,7 +676,7 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
       const int r = order[hb + h];
       const int64_t n = s.h_ptr[r + 1] - s.h_ptr[r];
       if (h > cur.h0 && batch_nnz + n > batch_limit) {
-        cur.h1 = h; cur.u1 = (int)units.size();
+        cur.h1 = h; cur.u1 = (int)n_units_total;
         s.batches.push_back(cur);
         cur = HeavyBatch{h, h, cur.u1, cur.u1};
         batch_nnz = 0;
@@ -637,14 +684,11 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
       batch_nnz += n;
       s.h_row_to_hrow[r] = h;
       hrow_id.push_back(r);
-      s.h_hrow_unit0.push_back((int)units.size());
-      int nunits = 0;
-      for (int64_t o = 0; o < n; o += s.slab, nunits++) {
-        eals::UnitDesc d;
-        d.off = s.h_ptr[r] + o; d.poff = poff + o; d.cnt = (int)std::min<int64_t>(s.slab, n - o);
-        d.row = r; d.hrow = h; d.slot = (int)units.size();
-        units.push_back(d);
-      }
+      s.h_hrow_unit0.push_back((int)n_units_total);
+      hrow_poff.push_back(poff);
+      const int nunits = (int)((n + s.slab - 1) / s.slab);
+      n_units_total += nunits;
+      if (n_units_total >= 0x7fffffffLL) return fail(EALS_ERR_UNSUPPORTED, "too many slabs of heavy rows");
       s.h_hrow_units.push_back(nunits);
       s.h_hrow_grp0.push_back((int)grp_unit0.size());
       s.h_hrow_grps.push_back((nunits + 31) / 32);
@@ -655,10 +699,10 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
       poff += n;
     }
     if (s.n_hrows) {
-      cur.h1 = s.n_hrows; cur.u1 = (int)units.size();
+      cur.h1 = s.n_hrows; cur.u1 = (int)n_units_total;
       s.batches.push_back(cur);
     }
-    s.n_units = (int)units.size();
+    s.n_units = (int)n_units_total;
     s.heavy_nnz = poff;
     s.max_batch_units = 0;
     for (const auto& b : s.batches) s.max_batch_units = std::max(s.max_batch_units, b.u1 - b.u0);
@@ -667,10 +711,15 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
       if (!v.empty()) CU(cudaMemcpyAsync(*d, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, m->stream));
       return EALS_OK;
     };
-    OK(dev_reserve(&s.units_canon, &s.cap_units_canon, std::max<size_t>(units.size(), 1)));
-    if (!units.empty())
-      CU(cudaMemcpyAsync(s.units_canon, units.data(), sizeof(eals::UnitDesc) * units.size(), cudaMemcpyHostToDevice, m->stream));
+    OK(dev_reserve(&s.units_canon, &s.cap_units_canon, std::max<size_t>((size_t)s.n_units, 1)));
     OK(up32(&s.hrow_id, &s.cap_hrow_id, hrow_id)); OK(up32(&s.hrow_unit0, &s.cap_hrow_unit0, s.h_hrow_unit0));
+    OK(dev_reserve(&s.hrow_poff, &s.cap_hrow_poff, std::max<size_t>(hrow_poff.size(), 1)));
+    if (s.n_units > 0) {
+      CU(cudaMemcpyAsync(s.hrow_poff, hrow_poff.data(), sizeof(int64_t) * hrow_poff.size(), cudaMemcpyHostToDevice, m->stream));
+      unit_fill_kernel<<<(s.n_units + 255) / 256, 256, 0, m->stream>>>(s.ptr, s.hrow_id, s.hrow_unit0, s.hrow_poff,
+                                                                       s.n_hrows, s.n_units, s.slab, s.units_canon);
+      OK(check_launch(m));
+    }
     OK(up32(&s.hrow_units, &s.cap_hrow_units, s.h_hrow_units));
     OK(up32(&s.hrow_grp0, &s.cap_hrow_grp0, s.h_hrow_grp0)); OK(up32(&s.hrow_grps, &s.cap_hrow_grps, s.h_hrow_grps));
     OK(up32(&s.grp_unit0, &s.cap_grp_unit0, grp_unit0)); OK(up32(&s.grp_cnt, &s.cap_grp_cnt, grp_cnt));
@@ -1361,7 +1410,7 @@ int eals_create(const eals_params* params, const int64_t* row_ptr, const int32_t
   TRY(dev_alloc(&m->SV, (size_t)m->LD * m->LD));
   TRY(dev_alloc(&m->Wi, (size_t)m->N));
   TRY(dev_alloc(&m->terms, 4));
-  TRY(dev_alloc(&m->flags, 8));
+  TRY(dev_alloc(&m->flags, 16));
   TRYCU(cudaMemsetAsync(m->U, 0, sizeof(double) * (size_t)m->M * m->LD, m->stream));
   TRYCU(cudaMemsetAsync(m->V, 0, sizeof(double) * (size_t)m->N * m->LD, m->stream));
   TRYCU(cudaMemsetAsync(m->SU, 0, sizeof(double) * (size_t)m->LD * m->LD, m->stream));
