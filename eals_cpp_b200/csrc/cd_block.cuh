@@ -310,26 +310,37 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
     __syncwarp();
     const int stages_in_loop = nblocks < 4 ? nblocks : 4;
 
-    if (!a.use_cache) {   // prediction cache from scratch: p_j = <x, y_j>
-      for (int fb = 0; fb < nblocks; fb++) {
-        stage_tile_rows(tile, rowp_s, n, n_pad, fb, lane, 32);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncwarp();
+    if (!a.use_cache) {
+      // Prediction cache from scratch, p_j = <x, y_j> (MF_fastALS.cpp:261-270): straight from global
+      // memory, 8 lanes per nonzero (16 bytes each of every 128-byte line of the gathered row), four
+      // nonzeros per step and every load independent — instead of staging block after block with a full
+      // memory round trip each (first sweep after setTrain: +60 ms on c4 before).
+      double* ptmp = reinterpret_cast<double*>(tile);   // the tile is free here
+      const int g8 = lane >> 3, gl = lane & 7;
+#pragma unroll 2
+      for (int j0 = 0; j0 < n; j0 += 4) {
+        const int j = j0 + g8;
+        double acc0 = 0.0, acc1 = 0.0;
+        if (j < n) {
+          const double* yrow = rowp_s[j];
 #pragma unroll
-        for (int m = 0; m < MAXM; m++) {
-          const int j = m * 32 + lane;
-          if (j < n) {
-            double y[16];
-            load_tile_row(tile, j, y);
-            double acc = pr[m];
-#pragma unroll
-            for (int e = 0; e < 16; e++) acc += x_s[fb * kFB + e] * y[e];
-            pr[m] = acc;
+          for (int c = 0; c < LD; c += kFB) {
+            const double2 d = ldg2(yrow + c + gl * 2);
+            acc0 += x_s[c + gl * 2] * d.x;
+            acc1 += x_s[c + gl * 2 + 1] * d.y;
           }
         }
-        __syncwarp();
+        double acc = acc0 + acc1;
+        acc += __shfl_xor_sync(kFullMask, acc, 1);
+        acc += __shfl_xor_sync(kFullMask, acc, 2);
+        acc += __shfl_xor_sync(kFullMask, acc, 4);
+        if (j < n && gl == 0) ptmp[j] = acc;
       }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < MAXM; m++)
+        if (m * 32 + lane < n) pr[m] = ptmp[m * 32 + lane];
+      __syncwarp();
     }
 
     stage_tile_rows(tile, rowp_s, n, n_pad, 0, lane, 32);
@@ -553,24 +564,32 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
 
   const int nblocks = (K + kFB - 1) / kFB;
 
-  // Pass 1: prediction cache p_j = <x, y_j> (skipped when the symmetric cache is valid)
-  for (int fb = 0; fb < (a.use_cache ? 0 : nblocks); fb++) {
-    stage_tile_rows(tile, rowp_s, n, n_pad, fb, tid, kT);
-    cp_async_commit();
-    cp_async_wait<0>();
+  // Pass 1: prediction cache p_j = <x, y_j> (skipped when the symmetric cache is valid): straight from
+  // global memory, 8 lanes per nonzero, all loads independent (see cd_warp_block_kernel)
+  if (!a.use_cache) {
+    const int g8 = tid >> 3, gl = tid & 7;
+    for (int j0 = 0; j0 < n; j0 += kT / 8) {
+      const int j = j0 + g8;
+      double acc0 = 0.0, acc1 = 0.0;
+      if (j < n) {
+        const double* yrow = rowp_s[j];
+#pragma unroll
+        for (int c = 0; c < LD; c += kFB) {
+          const double2 d = ldg2(yrow + c + gl * 2);
+          acc0 += x_s[c + gl * 2] * d.x;
+          acc1 += x_s[c + gl * 2 + 1] * d.y;
+        }
+      }
+      double acc = acc0 + acc1;
+      acc += __shfl_xor_sync(kFullMask, acc, 1);
+      acc += __shfl_xor_sync(kFullMask, acc, 2);
+      acc += __shfl_xor_sync(kFullMask, acc, 4);
+      if (j < n && gl == 0) z_s[j] = acc;
+    }
     __syncthreads();
 #pragma unroll
-    for (int m = 0; m < MW; m++) {
-      const int j = m * kT + tid;
-      if (j < n) {
-        double y[16];
-        load_tile_row(tile, j, y);
-        double acc = pr[m];
-#pragma unroll
-        for (int e = 0; e < 16; e++) acc += x_s[fb * kFB + e] * y[e];
-        pr[m] = acc;
-      }
-    }
+    for (int m = 0; m < MW; m++)
+      if (m * kT + tid < n) pr[m] = z_s[m * kT + tid];
     __syncthreads();
   }
 
