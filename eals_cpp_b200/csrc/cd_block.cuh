@@ -484,6 +484,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
     for (int st = stages_in_loop; st < 4; st++) fetch_next(st, slot + stride);   // K < 64: finish the chain here
     __syncwarp();
   }
+  peers_release(a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -715,6 +716,7 @@ cd_row_block_kernel(CdSide a, const int32_t* __restrict__ order, int first) {
       if (j < n) pc_store(a, p0 + j, pr[m]);
     }
   }
+  peers_release(a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -859,7 +861,7 @@ heavy_step_kernel(CdSide a, HeavyUnits hu, int u0, int fb, int nblocks, double* 
       }
       pr = (a0 + a1) + (a2 + a3);
       if (fb < nblocks) pred[poff + tid] = pr;
-      else if (a.pc_out.n) pc_store(a, off + tid, pr);   // final value -> symmetric cache
+      else if (a.pc_out.n) { pc_store(a, off + tid, pr); peers_release(a); }   // final value -> symmetric cache
     }
   } else if (a.use_cache && tid < n) {
     pred[poff + tid] = pr;   // the pipeline's compact cache starts from the symmetric one
@@ -998,6 +1000,7 @@ heavy_solve_kernel(CdSide a, HeavyUnits hu, int h0, int g0, int fb, const double
       delta[(size_t)h * 16 + ff] = livef ? xnew - xf : 0.0;
       if (livef) store_row_value(a, (size_t)grow * LD + f0 + ff, xnew);
     }
+    peers_release(a);
   }
 }
 

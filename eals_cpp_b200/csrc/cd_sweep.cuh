@@ -74,6 +74,16 @@ __device__ __forceinline__ void store_row_value(const CdSide& a, size_t off, dou
   for (int p = 0; p < a.peers.n; p++) a.peers.x[p][off] = v;
 }
 
+// Called by every thread of a sweep kernel after its last peer store: the stores are performed at
+// system scope before the thread exits, i.e. before the kernel counts as complete and the NCCL
+// all-reduce that orders them for the other ranks can start.  (Kernel completion should imply this; the
+// explicit fence costs one membar per thread per launch and removes the assumption.  One of five 8-GPU c4
+// runs of round 1 ended 0.19 % off in the loss after 8 epochs — not reproduced, cause not established;
+// profiles/README.md r01j.)
+__device__ __forceinline__ void peers_release(const CdSide& a) {
+  if (a.peers.n > 0 || a.pc_out.n > 1) __threadfence_system();
+}
+
 // Store a prediction at global position g of the other orientation's cache (on whichever rank holds it).
 __device__ __forceinline__ void pc_store_at(const CdSide& a, uint32_t g, double v) {
   int r = 0;
@@ -105,6 +115,7 @@ __global__ void pc_route_kernel(const double* __restrict__ stage, const uint32_t
 #pragma unroll
   for (int t = 1; t < 8; t++) r += (t < out.n && g >= out.bound[t]) ? 1 : 0;
   out.base[r][g - out.bound[r]] = stage[route_src[k]];
+  if (out.n > 1) __threadfence_system();   // see peers_release
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,6 +253,7 @@ cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count
     for (int m = 0; m < MAXM; m++)
       if (ok[m]) pc_store(a, p0 + m * 32 + lane, pr[m]);
   }
+  peers_release(a);
 }
 
 }  // namespace eals
