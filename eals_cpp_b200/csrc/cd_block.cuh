@@ -1,4 +1,5 @@
-// cd_block.cuh — K1 for long rows: BLOCKED coordinate descent.
+// cd_block.cuh — K1, the per-row coordinate descent of eALS as BLOCKED coordinate descent (all row
+// lengths; the plain one-reduction-per-factor form lives in cd_sweep.cuh for comparison).
 //
 // Same arithmetic as MF_fastALS::update_user_thread / update_item_thread (MF_fastALS.cpp:243-322,
 // 338-407), reorganised so that a row needs ONE team-wide reduction per block of 16 factors instead
@@ -19,20 +20,26 @@
 // (substitute p_j(current) = p_j + sum_{k<f} d_k y_jk into :297-305 and collect terms), followed by
 // p_j += sum_{f in B} d_f y_jf.  Only the floating-point summation order differs.
 //
-// G is GEMM-shaped (16 x n times n x 16) and goes to the fp64 tensor cores
-// (mma.sync.m8n8k4.f64, three 8 x 8 tiles: the upper-right one follows by symmetry); P, the
-// prediction-cache update and the 16-step solve are plain fp64.
+// G is GEMM-shaped (16 x n times n x 16) and goes to the fp64 tensor cores (mma.sync.m8n8k4.f64, three
+// 8 x 8 tiles — only the lower triangle of the symmetric system is needed); P rides along as two more
+// tiles (z in column 0 of the B operand); the prediction-cache update and the 16-step solve are plain
+// fp64.  On B200 a DMMA costs exactly 8 DFMAs of the one fp64 pipe (tests/micro/fp64_rate.cu).
 //
 // Data movement: the 128-byte line [f0, f0+16) of every gathered row is copied global -> shared with
 // cp.async (16 B per lane, 8 lanes per line: whole lines, no register staging), XOR-swizzled in
 // 16-byte chunks so that both the per-nonzero row reads (LDS.128) and the tensor-core fragment reads
-// are (nearly) conflict-free.
+// are conflict-free.  (TMA tile::gather4 writes the same layout and was measured: not faster here,
+// DESIGN.md §3.1.)
 //
-// Two drivers share the device code:
-//   * cd_row_block_kernel  — one CTA per row of 129..1024 nonzeros, everything on chip.
-//   * heavy_* kernels      — rows of any length split into slabs of 512 nonzeros; per block one
-//                            launch for the slab partials (+ the deferred cache update of the previous
-//                            block) and one for the per-row solve; prediction cache in HBM.
+// Three drivers share the device code (bucket limits in eals_b200.cu):
+//   * cd_warp_block_kernel — one WARP per row of 1..128 nonzeros (1..4 per lane), persistent CTAs, the
+//                            other side's S cache resident in shared memory, no CTA barrier per row.
+//   * cd_row_block_kernel  — one CTA per row of 129..512 nonzeros (4 warps x 2 or 3, 8 warps x 2 nonzeros
+//                            per thread), everything on chip.
+//   * heavy_* kernels      — rows of any length split into slabs of 128 nonzeros; per block one launch
+//                            for the slab partials (+ the deferred cache update of the previous block),
+//                            one for the grouped reduction and one for the per-row solve; prediction
+//                            cache in HBM; slabs launched in neighbour order for L2 reuse.
 #pragma once
 
 #include "cd_sweep.cuh"
