@@ -121,6 +121,45 @@ def allreduce_sum(t, group=None) -> None:
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+def gather_full_array(host, n: int, rank: int, world: int, device, buf=None, group=None):
+    """Every rank needs the FULL array ``host[:n]`` (a numpy array every rank holds in host memory) on
+    its device.  Rank r copies only the r-th 1/world chunk from the host and an all-gather completes the
+    array on every rank (NCCL over NVLink for CUDA tensors; gloo on CPU in the tests): the host-to-device
+    bytes of a rank shrink by ``world``.  Returns (tensor of n elements, the padded buffer to reuse)."""
+    import torch
+    import torch.distributed as dist
+    dt = torch.from_numpy(np.empty(0, host.dtype)).dtype
+    per = max(1, (n + world - 1) // world)
+    if buf is None or buf.numel() < per * world or buf.dtype != dt or str(buf.device) != str(torch.device(device)):
+        buf = torch.empty(per * world, dtype=dt, device=device)
+    full = buf[:per * world]
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    chunk = full[rank * per:(rank + 1) * per]
+    if hi > lo:
+        chunk[:hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(host[lo:hi])), non_blocking=True)
+    dist.all_gather_into_tensor(full, chunk, group=group)
+    return full[:max(n, 1)], buf
+
+
+def insert_interaction(sm: "SparseMat", u: int, i: int):
+    """The host arrays of ``sm`` with the entry (u, i), rating 1, added at its sorted position in both
+    orientations (what ``trainMatrix.setValue(u, i, 1)`` of MF_fastALS.cpp:224 means); None if the entry
+    is already there."""
+    rp, ci, cp, ri, rv, cv = sm.row_ptr, sm.col_idx, sm.col_ptr, sm.row_idx, sm.row_val, sm.col_val
+    a, b = int(rp[u]), int(rp[u + 1])
+    k = a + int(np.searchsorted(ci[a:b], i))
+    if k < b and ci[k] == i:
+        return None
+    a2, b2 = int(cp[i]), int(cp[i + 1])
+    k2 = a2 + int(np.searchsorted(ri[a2:b2], u))
+    ci = np.insert(ci, k, np.int32(i)); ri = np.insert(ri, k2, np.int32(u))
+    rp = rp.copy(); rp[u + 1:] += 1
+    cp = cp.copy(); cp[i + 1:] += 1
+    if rv is not None:
+        rv = np.insert(rv, k, 1.0); cv = np.insert(cv, k2, 1.0)
+    return SparseMat(sm.M, sm.N, rp, ci, cp, ri, rv, cv)
+
+
 class _DevArray:
     """Expose a raw device pointer to torch through __cuda_array_interface__."""
 
@@ -247,30 +286,20 @@ class MF_fastALS:
         host-to-device bytes of a rank shrink by world (measured before, c4: setTrain 0.5 s at 2 ranks,
         2.1 s at 8).  The device buffers are kept for the next setTrain."""
         import torch
-        import torch.distributed as dist
         dev = f"cuda:{self.device}"
         W, r = self.world, self.rank
         nnz = int(sm.row_ptr[-1])
-        per = max(1, (nnz + W - 1) // W)
-        kinds = [("ci", sm.col_idx, torch.int32), ("ri", sm.row_idx, torch.int32)]
+        kinds = [("ci", sm.col_idx), ("ri", sm.row_idx)]
         if sm.row_val is not None:
-            kinds += [("rv", sm.row_val, torch.float64), ("cv", sm.col_val, torch.float64)]
+            kinds += [("rv", sm.row_val), ("cv", sm.col_val)]
         bufs = self.__dict__.setdefault("_full_bufs", {})
         out = {}
-        for name, host, dt in kinds:
-            full = bufs.get(name)
-            if full is None or full.numel() < per * W or full.dtype != dt:
-                full = bufs[name] = torch.empty(per * W, dtype=dt, device=dev)
-            full = full[:per * W]
-            lo, hi = min(r * per, nnz), min((r + 1) * per, nnz)
-            chunk = full[r * per:(r + 1) * per]
-            if hi > lo:
-                chunk[:hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(host[lo:hi])), non_blocking=True)
-            dist.all_gather_into_tensor(full, chunk, group=self.group)
-            out[name] = full[:max(nnz, 1)]
+        for name, host in kinds:
+            out[name], bufs[name] = gather_full_array(host, nnz, r, W, dev, bufs.get(name), self.group)
         rp = torch.from_numpy(np.ascontiguousarray(sm.row_ptr, np.int64)).to(dev)
         cp = torch.from_numpy(np.ascontiguousarray(sm.col_ptr, np.int64)).to(dev)
-        self._h2d_bytes_last = sum(min(per, max(0, nnz - r * per)) * (4 if n in ("ci", "ri") else 8) for n, _, _ in kinds) \
+        per = max(1, (nnz + W - 1) // W)
+        self._h2d_bytes_last = sum(min(per, max(0, nnz - r * per)) * host.dtype.itemsize for _, host in kinds) \
             + 8 * (sm.M + 1 + sm.N + 1)
         return SparseMat(sm.M, sm.N, rp, out["ci"], cp, out["ri"], out.get("rv"), out.get("cv"))
 
@@ -458,19 +487,11 @@ class MF_fastALS:
             raise IndexError("updateModel: (u, i) outside the matrix")
         sm = self.trainMatrix
         host = lambda a: None if a is None else (a if isinstance(a, np.ndarray) else a.cpu().numpy())
-        rp, ci, cp, ri = host(sm.row_ptr), host(sm.col_idx), host(sm.col_ptr), host(sm.row_idx)
-        rv, cv = host(sm.row_val), host(sm.col_val)
-        a, b = int(rp[u]), int(rp[u + 1])
-        k = a + int(np.searchsorted(ci[a:b], i))
-        if not (k < b and ci[k] == i):                     # trainMatrix.setValue(u, i, 1); W.setValue(u, i, w_new)
-            a2, b2 = int(cp[i]), int(cp[i + 1])
-            k2 = a2 + int(np.searchsorted(ri[a2:b2], u))
-            ci = np.insert(ci, k, np.int32(i)); ri = np.insert(ri, k2, np.int32(u))
-            rp = rp.copy(); rp[u + 1:] += 1
-            cp = cp.copy(); cp[i + 1:] += 1
-            if rv is not None:
-                rv = np.insert(rv, k, 1.0); cv = np.insert(cv, k2, 1.0)
-            self.setTrain(SparseMat(sm.M, sm.N, rp, ci, cp, ri, rv, cv))
+        sm = SparseMat(sm.M, sm.N, host(sm.row_ptr), host(sm.col_idx), host(sm.col_ptr), host(sm.row_idx),
+                       host(sm.row_val), host(sm.col_val))
+        grown = insert_interaction(sm, u, i)              # trainMatrix.setValue(u, i, 1); W.setValue(u, i, w_new)
+        if grown is not None:
+            self.setTrain(grown)
         Wi = self.Wi
         if Wi[i] == 0.0:                                    # a new item: weight and its term in the SV cache
             Wi[i] = self.w0 / self.itemCount

@@ -85,7 +85,16 @@ def _worker(rank, world, port, q):
         S = mine.T @ mine
         allreduce_sum(S)
         ok_gram = bool(torch.allclose(S, truth.T @ truth, rtol=1e-14))
-        q.put((rank, ok_rows, ok_gram, bounds))
+        # setTrain on several ranks: each rank copies 1/world of an index array, the all-gather completes it
+        from eals_cpp_b200.model import gather_full_array
+        ok_gather = True
+        for n in (1, 7, 64, 1001):
+            host = (np.arange(n, dtype=np.int32) * 3 + 1)
+            full, buf = gather_full_array(host, n, rank, world, "cpu")
+            ok_gather &= bool(np.array_equal(full.numpy()[:n], host))
+            full2, buf2 = gather_full_array(host[::-1].copy(), n, rank, world, "cpu", buf)   # buffer reuse
+            ok_gather &= buf2 is buf and bool(np.array_equal(full2.numpy()[:n], host[::-1]))
+        q.put((rank, ok_rows, ok_gram and ok_gather, bounds))
     finally:
         dist.destroy_process_group()
 
@@ -104,3 +113,38 @@ def test_exchange_and_gram_allreduce_world2_gloo():
         assert p.exitcode == 0
     assert all(r[1] and r[2] for r in res), res
     assert res[0][3] == res[1][3]
+
+
+def test_insert_interaction_keeps_both_orientations_sorted():
+    """Host part of the online updateModel (MF_fastALS.cpp:223-224): the new entry lands at its sorted
+    position in the CSR and in the CSC arrays; an existing entry changes nothing."""
+    from eals_cpp_b200.model import SparseMat, insert_interaction
+    from conftest import random_csr
+    M, N = 40, 30
+    row_ptr, col_idx = random_csr(M, N, 5, seed=3, empty_frac=0.1)
+    sm = SparseMat.from_csr(M, N, row_ptr, col_idx)
+    dense = np.zeros((M, N), bool)
+    for u in range(M):
+        dense[u, col_idx[row_ptr[u]:row_ptr[u + 1]]] = True
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        u, i = int(rng.integers(M)), int(rng.integers(N))
+        grown = insert_interaction(sm, u, i)
+        if dense[u, i]:
+            assert grown is None
+            continue
+        dense[u, i] = True
+        sm = grown
+        want = SparseMat.from_csr(M, N, *_csr_of(dense))
+        for a, b in ((sm.row_ptr, want.row_ptr), (sm.col_idx, want.col_idx), (sm.col_ptr, want.col_ptr), (sm.row_idx, want.row_idx)):
+            assert np.array_equal(a, b)
+    vals = SparseMat.from_csr(M, N, sm.row_ptr, sm.col_idx, np.full(sm.nnz, 2.0))
+    u, i = np.argwhere(~dense)[0]
+    g = insert_interaction(vals, int(u), int(i))
+    assert g.row_val.sum() == 2.0 * sm.nnz + 1.0 and g.col_val.sum() == g.row_val.sum()   # rating 1 = w_new
+
+
+def _csr_of(dense):
+    row_ptr = np.concatenate([[0], np.cumsum(dense.sum(1))]).astype(np.int64)
+    col_idx = np.concatenate([np.flatnonzero(r) for r in dense]).astype(np.int32)
+    return row_ptr, col_idx
