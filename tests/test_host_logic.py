@@ -148,3 +148,46 @@ def _csr_of(dense):
     row_ptr = np.concatenate([[0], np.cumsum(dense.sum(1))]).astype(np.int64)
     col_idx = np.concatenate([np.flatnonzero(r) for r in dense]).astype(np.int32)
     return row_ptr, col_idx
+
+
+def test_update_model_host_flow_with_a_mocked_library():
+    """updateModel's host side (MF_fastALS.cpp:223-242) without a GPU: the matrix handed to setTrain has the
+    new entry, a brand-new item gets w0 / itemCount, and the 10 alternating row updates are each followed by
+    their S patch."""
+    from eals_cpp_b200 import model as mdl
+    from conftest import random_csr
+    M, N = 30, 20
+    row_ptr, col_idx = random_csr(M, N, 4, seed=1)
+    keep = [[c for c in col_idx[row_ptr[u]:row_ptr[u + 1]] if c != 3] for u in range(M)]      # item 3 unseen
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in keep])]).astype(np.int64)
+    col_idx = np.array([c for r in keep for c in r], np.int32)
+    calls = []
+
+    class Fake(mdl.MF_fastALS):
+        def __init__(self):                          # no library, no device
+            self.world, self.userCount, self.itemCount, self.w0 = 1, M, N, 10.0
+            self.trainMatrix = mdl.SparseMat.from_csr(M, N, row_ptr, col_idx)
+            self._wi = np.ones(N); self._wi[3] = 0.0
+        Wi = property(lambda self: self._wi.copy(), lambda self, w: (calls.append(("Wi", w.copy())), setattr(self, "_wi", w)))
+        def setTrain(self, sm): calls.append(("setTrain", sm)); self.trainMatrix = sm
+        def _factor_row(self, which, r): return np.full(4, float(len(calls)))
+        def update_user_thread(self, u): calls.append(("user", u))
+        def update_item_thread(self, i): calls.append(("item", i))
+        def update_user_SU(self, old, new): calls.append(("SU", old[0] < new[0]))
+        def update_item_SV(self, i, old, new): calls.append(("SV", i))
+        def close(self): pass
+
+    f = Fake()
+    f.updateModel(5, 3)
+    kinds = [c[0] for c in calls]
+    assert kinds[0] == "setTrain" and kinds[1] == "Wi"
+    sm = calls[0][1]
+    assert 3 in sm.col_idx[sm.row_ptr[5]:sm.row_ptr[6]] and sm.nnz == len(col_idx) + 1
+    assert 5 in sm.row_idx[sm.col_ptr[3]:sm.col_ptr[4]]
+    assert calls[1][1][3] == 10.0 / N
+    assert kinds[2:] == ["user", "SU", "item", "SV"] * 10
+    calls.clear()
+    f.updateModel(5, 3, patch_S=False)                # already present: no setTrain, weight already set, stale caches
+    assert [c[0] for c in calls] == ["user", "item"] * 10
+    with pytest.raises(IndexError):
+        f.updateModel(M, 0)
