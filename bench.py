@@ -342,6 +342,7 @@ def main():
                 "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": sweep_ms, "peak_source": peak_src}
 
     loss = fals.loss()
+    replicas_ok = fals.replicas_consistent()    # every rank's U and V replicas bit-identical (hash on device)
 
     # ---- e2e: through the public API with HOST buffers -------------------------------------------------
     e2e = None
@@ -408,7 +409,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items() if phase_calls[k]},
             "sweep_detail_ms_per_step": {k: v / args.steps for k, v in detail_ms.items()},
-            "loss_after": loss,
+            "loss_after": loss, "replicas_consistent": replicas_ok,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

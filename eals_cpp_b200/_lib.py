@@ -50,6 +50,8 @@ SIGNATURES = {
     "eals_init_factors": (C.c_int, [_P]),
     "eals_set_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
     "eals_get_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "eals_save_factors": (C.c_int, [_P, C.c_char_p]),
+    "eals_load_factors": (C.c_int, [_P, C.c_char_p]),
     "eals_get_factor_row": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "eals_set_item_weights": (C.c_int, [_P, C.c_int32, _P]),
     "eals_get_item_weights": (C.c_int, [_P, C.c_int32, _P]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "eals_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "eals_set_stream": (C.c_int, [_P, _P, C.c_int32]),
     "eals_sync": (C.c_int, [_P]),
+    "eals_factor_hash": (C.c_int, [_P, _P]),
     "eals_ipc_handle": (C.c_int, [_P, C.c_int32, _P]),
     "eals_ipc_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "eals_ipc_detach": (C.c_int, [_P]),

@@ -118,142 +118,4 @@ __global__ void pc_route_kernel(const double* __restrict__ stage, const uint32_t
   if (out.n > 1) __threadfence_system();   // see peers_release
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-per-row kernel: rows with 1..32*MAXM nonzeros.  Lane l owns nonzeros l, l+32, ...; their
-// prediction cache, weights and the current column value stay in registers.  Per factor: one
-// shared-memory column read per owned nonzero, a K/32-long slice of the S-row dot product, one
-// paired warp reduction (numerator, denominator), one fp64 divide.
-// ---------------------------------------------------------------------------------------------
-template <int LD, int MAXM>
-struct CdWarpSmem {
-  static constexpr int kRows = 32 * MAXM;
-  static constexpr int kBytesPerWarp = kRows * kTilePad * 8 + LD * 8 + kRows * 4;
-};
-
-template <int LD, int MAXM>
-__device__ __forceinline__ void stage_block(double* tile, const int* idx_s, const double* __restrict__ Y,
-                                            int n, int fb) {
-  const int lane = lane_id();
-  const int n8 = n * 8;  // 16-byte chunks in this block: 8 per gathered row
-  for (int t0 = lane; t0 < n8; t0 += 128) {
-    double2 d[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int t = t0 + q * 32;
-      if (t < n8) d[q] = ldg2(Y + (size_t)idx_s[t >> 3] * LD + fb * kFB + (t & 7) * 2);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int t = t0 + q * 32;
-      if (t < n8) {
-        double* dst = tile + (t >> 3) * kTilePad + (t & 7) * 2;
-        dst[0] = d[q].x;
-        dst[1] = d[q].y;
-      }
-    }
-  }
-}
-
-template <int LD, int MAXM, bool USER>
-__global__ void __launch_bounds__(128)
-cd_warp_kernel(CdSide a, const int32_t* __restrict__ order, int first, int count) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Sm = CdWarpSmem<LD, MAXM>;
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (slot >= count) return;  // warp-uniform; no block-wide barrier is used below
-
-  double* tile = reinterpret_cast<double*>(smem_raw + (size_t)warp * Sm::kBytesPerWarp);
-  double* u_s = tile + Sm::kRows * kTilePad;
-  int* idx_s = reinterpret_cast<int*>(u_s + LD);
-
-  const int row = order[first + slot];
-  const int64_t p0 = a.ptr[row];
-  const int n = (int)(a.ptr[row + 1] - p0);
-  const int grow = a.row_base + row;
-  double* xrow = a.X + (size_t)grow * LD;
-  const int K = a.K;
-  const double wi_row = USER ? 0.0 : a.Wi[grow];
-
-  for (int k = lane; k < LD; k += 32) u_s[k] = xrow[k];
-
-  double wr[MAXM], cw[MAXM], pr[MAXM], vv[MAXM];
-  bool ok[MAXM];
-#pragma unroll
-  for (int m = 0; m < MAXM; m++) {
-    const int j = m * 32 + lane;
-    ok[m] = j < n;
-    wr[m] = cw[m] = pr[m] = vv[m] = 0.0;
-    if (ok[m]) {
-      const int id = a.idx[p0 + j];
-      idx_s[j] = id;
-      const double w = a.val ? a.val[p0 + j] : 1.0;
-      wr[m] = w * w;                                   // w_ui * r_ui, both are the stored value
-      cw[m] = w - (USER ? a.Wi[id] : wi_row);
-      if (a.use_cache) pr[m] = a.pc_in[p0 + j];
-    }
-  }
-  __syncwarp();
-
-  const int nblocks = (K + kFB - 1) / kFB;
-
-  // Pass 1: prediction cache  pred_j = <x, y_j>, accumulated in factor order.
-  for (int fb = 0; fb < (a.use_cache ? 0 : nblocks); fb++) {
-    stage_block<LD, MAXM>(tile, idx_s, a.Y, n, fb);
-    __syncwarp();
-#pragma unroll
-    for (int fl = 0; fl < kFB; fl++) {
-      const double uf = u_s[fb * kFB + fl];
-#pragma unroll
-      for (int m = 0; m < MAXM; m++)
-        if (ok[m]) pr[m] += uf * tile[(m * 32 + lane) * kTilePad + fl];
-    }
-    __syncwarp();
-  }
-
-  // Pass 2: the K sequential coordinate updates.
-  for (int fb = 0; fb < nblocks; fb++) {
-    stage_block<LD, MAXM>(tile, idx_s, a.Y, n, fb);
-    __syncwarp();
-    const int fend = min(kFB, K - fb * kFB);
-    for (int fl = 0; fl < fend; fl++) {
-      const int f = fb * kFB + fl;
-      const double uf = u_s[f];
-      const double* __restrict__ Srow = a.S + (size_t)f * LD;
-      double np = 0.0, dp = 0.0;
-      for (int k = lane; k < K; k += 32)
-        if (k != f) np -= u_s[k] * __ldg(Srow + k);
-      if (!USER) np *= wi_row;
-#pragma unroll
-      for (int m = 0; m < MAXM; m++) {
-        if (ok[m]) {
-          const double v = tile[(m * 32 + lane) * kTilePad + fl];
-          const double pm = pr[m] - uf * v;
-          np += (wr[m] - cw[m] * pm) * v;
-          dp += cw[m] * v * v;
-          pr[m] = pm;
-          vv[m] = v;
-        }
-      }
-      warp_sum_pair(np, dp);
-      const double sff = __ldg(Srow + f);
-      dp += (USER ? sff : wi_row * sff) + a.reg;
-      const double unew = np / dp;
-#pragma unroll
-      for (int m = 0; m < MAXM; m++)
-        if (ok[m]) pr[m] += unew * vv[m];
-      __syncwarp();
-      if (lane == 0) u_s[f] = unew;
-      __syncwarp();
-    }
-  }
-  for (int k = lane; k < K; k += 32) store_row_value(a, (size_t)grow * LD + k, u_s[k]);
-  if (a.pc_out.n) {
-#pragma unroll
-    for (int m = 0; m < MAXM; m++)
-      if (ok[m]) pc_store(a, p0 + m * 32 + lane, pr[m]);
-  }
-  peers_release(a);
-}
-
 }  // namespace eals

@@ -187,6 +187,8 @@ struct eals_model {
   double acc_ms[T_COUNT] = {0};
   int64_t acc_calls[T_COUNT] = {0};
   bool factors_set = false;
+  bool su_fresh = true;          // SU describes the current U (false after single-row user updates without a Gram)
+  double* S_tmp = nullptr;       // [LD][LD] scratch Gram for loss() while SU is stale
   int* flags = nullptr;          // [8] device scratch for validation kernels (no malloc/free per call)
   eals::PeerSet peersU = {}, peersV = {};   // IPC mappings of the other ranks' U / V replicas
   // symmetric prediction cache (single-rank models only)
@@ -825,18 +827,6 @@ void toc(eals_model* m, int which) {
   }
 
 template <int LD, int MAXM, bool USER>
-int launch_cd_warp(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
-  if (count <= 0) return EALS_OK;
-  using Sm = eals::CdWarpSmem<LD, MAXM>;
-  constexpr int kWarps = 4;
-  const size_t smem = (size_t)Sm::kBytesPerWarp * kWarps;
-  auto kern = eals::cd_warp_kernel<LD, MAXM, USER>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(count + kWarps - 1) / kWarps, kWarps * 32, smem, m->stream>>>(a, order, first, count);
-  return check_launch(m);
-}
-
-template <int LD, int MAXM, bool USER>
 int launch_cd_warp_block(eals_model* m, const CdSide& a, const int32_t* order, int first, int count) {
   if (count <= 0) return EALS_OK;
   using Sm = eals::WarpBlockSmem<LD, MAXM>;
@@ -938,19 +928,11 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   OK((launch_cd_row_block<LD, 4, 2, USER>(m, a, s.order, s.first[5], s.first[6] - s.first[5])));   // 129..256
   toc(m, t0 + 1);
   tic(m, t0 + 2);
-  // EALS_WARP_SEQ=1: the plain sequential form (one reduction + one divide per factor) for A/B runs;
-  // measured on c4 it is 2.6x slower than the blocked form (profiles/README.md r01h)
-  static const bool seq = getenv("EALS_WARP_SEQ") && getenv("EALS_WARP_SEQ")[0] == '1';
-  if (seq) {
-    OK((launch_cd_warp<LD, 4, USER>(m, a, s.order, s.first[3], s.first[5] - s.first[3])));
-    OK((launch_cd_warp<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
-    OK((launch_cd_warp<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
-  } else {   // one warp per row up to 128 nonzeros: no CTA barrier anywhere in the row loop
-    OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
-    OK((launch_cd_warp_block<LD, 3, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
-    OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
-    OK((launch_cd_warp_block<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
-  }
+  // one warp per row up to 128 nonzeros: no CTA barrier anywhere in the row loop
+  OK((launch_cd_warp_block<LD, 4, USER>(m, a, s.order, s.first[4], s.first[5] - s.first[4])));
+  OK((launch_cd_warp_block<LD, 3, USER>(m, a, s.order, s.first[3], s.first[4] - s.first[3])));
+  OK((launch_cd_warp_block<LD, 2, USER>(m, a, s.order, s.first[2], s.first[3] - s.first[2])));
+  OK((launch_cd_warp_block<LD, 1, USER>(m, a, s.order, s.first[1], s.first[2] - s.first[1])));
   toc(m, t0 + 2);
   return EALS_OK;
 }
@@ -971,6 +953,7 @@ int sweep(eals_model* m, bool user, int only_row) {
   a.peers = user ? m->peersU : m->peersV;
   if (only_row >= 0) {
     m->pc_u_valid = m->pc_i_valid = false;   // a single-row update changes factors behind the cache's back
+    if (user) m->su_fresh = false;           // ... and U behind SU's back (MF_fastALS.cpp:243-322 never touches SU)
   } else if (m->pcache_on && m->pc_attached) {
     bool& in_valid = user ? m->pc_u_valid : m->pc_i_valid;
     bool& out_valid = user ? m->pc_i_valid : m->pc_u_valid;
@@ -1014,7 +997,23 @@ int gram(eals_model* m, bool user, bool full) {
   const int r1 = full ? (user ? m->M : m->N) : (user ? m->ue : m->ie);
   double* S = user ? m->SU : m->SV;
   DISPATCH_LD(m->LD, OK(launch_gram<LD>(m, X, w, r0, r1, S)));
+  if (user) m->su_fresh = true;
   return sync_if_debug(m);
+}
+
+// Position-dependent 64-bit checksum of a buffer of doubles: sum over t of mix(bits[t] ^ t * golden) mod 2^64 —
+// an associative sum, so the result does not depend on the thread schedule.  Used to prove that the U / V
+// replicas of all ranks are bit-identical (eals_factor_hash).
+__global__ void hash_doubles_kernel(const double* __restrict__ x, size_t n, unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long v = (unsigned long long)__double_as_longlong(x[t]) ^ ((unsigned long long)t * 0x9E3779B97F4A7C15ull);
+    v ^= v >> 30; v *= 0xBF58476D1CE4E5B9ull; v ^= v >> 27; v *= 0x94D049BB133111EBull; v ^= v >> 31;   // splitmix64 finaliser
+    acc += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(eals::kFullMask, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 // Scatter dense [n][K] (host or device) into the padded [n][LD] device layout and back.
@@ -1122,7 +1121,16 @@ int loss_terms(eals_model* m, double terms[4]) {
   OK(check_launch(m));
   eals::sum_partials_kernel<<<1, 256, 0, m->stream>>>(m->partials, g, m->terms + 2, 0);
   OK(check_launch(m));
-  eals::frob_inner_kernel<<<1, 256, 0, m->stream>>>(m->SU, m->SV, m->K, m->LD, m->terms + 3);
+  // sum_u u^T SV u (MF_fastALS.cpp:199-200) = <U^T U, SV>_F.  The cached SU is U^T U only while it is
+  // fresh; after single-row updates (update_user_thread / updateModel, which leave SU alone as the
+  // reference does) the Gram of the CURRENT U goes to a scratch block — SU itself must stay stale.
+  const double* su_now = m->SU;
+  if (!m->su_fresh) {
+    if (!m->S_tmp) OK(dev_alloc(&m->S_tmp, (size_t)m->LD * m->LD));
+    DISPATCH_LD(m->LD, OK(launch_gram<LD>(m, m->U, nullptr, 0, m->M, m->S_tmp)));
+    su_now = m->S_tmp;
+  }
+  eals::frob_inner_kernel<<<1, 256, 0, m->stream>>>(su_now, m->SV, m->K, m->LD, m->terms + 3);
   OK(check_launch(m));
   toc(m, T_LOSS);
   CU(cudaMemcpyAsync(terms, m->terms, 4 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -1341,7 +1349,7 @@ int eals_destroy(eals_model* m) {
   free_side(m->users);
   free_side(m->items);
   cudaFree(m->U); cudaFree(m->V); cudaFree(m->SU); cudaFree(m->SV); cudaFree(m->Wi);
-  cudaFree(m->terms); cudaFree(m->partials); cudaFree(m->flags);
+  cudaFree(m->terms); cudaFree(m->partials); cudaFree(m->flags); cudaFree(m->S_tmp);
   cudaFree(m->pc_u); cudaFree(m->pc_i); cudaFree(m->map_u); cudaFree(m->map_i);
   cudaFree(m->pc_stage_u); cudaFree(m->pc_stage_i);
   cudaFree(m->route_src_u); cudaFree(m->route_dst_u); cudaFree(m->route_src_i); cudaFree(m->route_dst_i);
@@ -1486,6 +1494,87 @@ int eals_get_factors(eals_model* m, int32_t space, double* U, double* V) {
   if (U) OK(download_dense(m, U, m->U, (size_t)m->M, space));
   if (V) OK(download_dense(m, V, m->V, (size_t)m->N, space));
   return EALS_OK;
+}
+
+namespace {
+struct CkptHeader {
+  char magic[8];
+  int32_t version, factors;
+  int64_t n_users, n_items;
+};
+constexpr char kCkptMagic[8] = {'E', 'A', 'L', 'S', 'B', '2', '0', '0'};
+constexpr size_t kCkptChunkRows = 1 << 18;
+}  // namespace
+
+int eals_save_factors(eals_model* m, const char* path) {
+  if (!m || !path) return fail(EALS_ERR_ARG, "null argument");
+  if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised");
+  CU(cudaSetDevice(m->p.device));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(EALS_ERR_ARG, "cannot open %s for writing", path);
+  CkptHeader h;
+  std::memcpy(h.magic, kCkptMagic, 8);
+  h.version = 1; h.factors = m->K; h.n_users = m->M; h.n_items = m->N;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  std::vector<double> buf(kCkptChunkRows * (size_t)m->K);
+  int rc = EALS_OK;
+  for (int side = 0; side < 2 && ok && rc == EALS_OK; side++) {
+    const size_t n = side == 0 ? (size_t)m->M : (size_t)m->N;
+    const double* src = side == 0 ? m->U : m->V;
+    for (size_t r0 = 0; r0 < n && ok && rc == EALS_OK; r0 += kCkptChunkRows) {
+      const size_t nr = std::min(kCkptChunkRows, n - r0);
+      rc = download_dense(m, buf.data(), src + r0 * m->LD, nr, EALS_HOST);
+      ok = rc == EALS_OK && fwrite(buf.data(), sizeof(double), nr * m->K, f) == nr * m->K;
+    }
+  }
+  if (ok && rc == EALS_OK) {
+    std::vector<double> wi((size_t)m->N);
+    rc = eals_get_item_weights(m, EALS_HOST, wi.data());
+    ok = rc == EALS_OK && fwrite(wi.data(), sizeof(double), wi.size(), f) == wi.size();
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (rc != EALS_OK) return rc;
+  return ok ? EALS_OK : fail(EALS_ERR_ARG, "short write to %s", path);
+}
+
+int eals_load_factors(eals_model* m, const char* path) {
+  if (!m || !path) return fail(EALS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->p.device));
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(EALS_ERR_ARG, "cannot open %s", path);
+  CkptHeader h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, kCkptMagic, 8) != 0 || h.version != 1) {
+    fclose(f);
+    return fail(EALS_ERR_ARG, "%s is not an eals_b200 factor checkpoint (version 1)", path);
+  }
+  if (h.factors != m->K || h.n_users != m->M || h.n_items != m->N) {
+    fclose(f);
+    return fail(EALS_ERR_ARG, "checkpoint is %lld x %lld, K=%d; the model is %d x %d, K=%d", (long long)h.n_users,
+                (long long)h.n_items, h.factors, m->M, m->N, m->K);
+  }
+  std::vector<double> buf(kCkptChunkRows * (size_t)m->K);
+  int rc = EALS_OK;
+  bool ok = true;
+  for (int side = 0; side < 2 && ok && rc == EALS_OK; side++) {
+    const size_t n = side == 0 ? (size_t)m->M : (size_t)m->N;
+    double* dst = side == 0 ? m->U : m->V;
+    for (size_t r0 = 0; r0 < n && ok && rc == EALS_OK; r0 += kCkptChunkRows) {
+      const size_t nr = std::min(kCkptChunkRows, n - r0);
+      ok = fread(buf.data(), sizeof(double), nr * m->K, f) == nr * m->K;
+      if (ok) rc = upload_dense(m, dst + r0 * m->LD, buf.data(), nr, EALS_HOST);
+      if (rc == EALS_OK && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = fail(EALS_ERR_CUDA, "checkpoint upload");
+    }
+  }
+  std::vector<double> wi((size_t)m->N);
+  if (ok && rc == EALS_OK) ok = fread(wi.data(), sizeof(double), wi.size(), f) == wi.size();
+  fclose(f);
+  if (rc != EALS_OK) return rc;
+  if (!ok) return fail(EALS_ERR_ARG, "%s is truncated", path);
+  m->factors_set = true;
+  m->pc_u_valid = m->pc_i_valid = false;
+  CU(cudaMemcpyAsync(m->Wi, wi.data(), sizeof(double) * m->N, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return eals_refresh_S(m);
 }
 
 int eals_get_factor_row(eals_model* m, int32_t which, int32_t row, double* out) {
@@ -1780,6 +1869,23 @@ int eals_ipc_attach(eals_model* m, int32_t which, int32_t n_peers, const void* h
     CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     ps.x[ps.n++] = (double*)ptr;
   }
+  return EALS_OK;
+}
+
+int eals_factor_hash(eals_model* m, uint64_t out[2]) {
+  if (!m || !out) return fail(EALS_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->p.device));
+  OK(ensure_partials(m, 16));
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(m->partials);
+  CU(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), m->stream));
+  hash_doubles_kernel<<<4 * m->sm_count, 256, 0, m->stream>>>(m->U, (size_t)m->M * m->LD, d);
+  OK(check_launch(m));
+  hash_doubles_kernel<<<4 * m->sm_count, 256, 0, m->stream>>>(m->V, (size_t)m->N * m->LD, d + 1);
+  OK(check_launch(m));
+  unsigned long long h[2];
+  CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  out[0] = h[0]; out[1] = h[1];
   return EALS_OK;
 }
 

@@ -143,15 +143,21 @@ def gather_full_array(host, n: int, rank: int, world: int, device, buf=None, gro
 
 def insert_interaction(sm: "SparseMat", u: int, i: int):
     """The host arrays of ``sm`` with the entry (u, i), rating 1, added at its sorted position in both
-    orientations (what ``trainMatrix.setValue(u, i, 1)`` of MF_fastALS.cpp:224 means); None if the entry
-    is already there."""
+    orientations (what ``trainMatrix.setValue(u, i, 1)`` / ``W.setValue(u, i, w_new)`` of
+    MF_fastALS.cpp:224-226 mean).  An entry that is already there has its rating (= weight) overwritten
+    with 1, as setValue does; None if nothing changes (entry present with rating 1)."""
     rp, ci, cp, ri, rv, cv = sm.row_ptr, sm.col_idx, sm.col_ptr, sm.row_idx, sm.row_val, sm.col_val
     a, b = int(rp[u]), int(rp[u + 1])
     k = a + int(np.searchsorted(ci[a:b], i))
-    if k < b and ci[k] == i:
-        return None
     a2, b2 = int(cp[i]), int(cp[i + 1])
     k2 = a2 + int(np.searchsorted(ri[a2:b2], u))
+    if k < b and ci[k] == i:
+        if rv is None or rv[k] == 1.0:
+            return None
+        rv, cv = rv.copy(), cv.copy()
+        rv[k] = 1.0
+        cv[k2] = 1.0
+        return SparseMat(sm.M, sm.N, rp, ci, cp, ri, rv, cv)
     ci = np.insert(ci, k, np.int32(i)); ri = np.insert(ri, k2, np.int32(u))
     rp = rp.copy(); rp[u + 1:] += 1
     cp = cp.copy(); cp[i + 1:] += 1
@@ -243,6 +249,7 @@ class MF_fastALS:
             self._attach_peers()
         if init:
             check(self.lib.eals_init_factors(self.h))     # MF_fastALS.cpp:85-90
+            self._replicas_written()
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _attach_peers(self, factors=True):
@@ -277,6 +284,17 @@ class MF_fastALS:
             others = np.ascontiguousarray(np.concatenate([allh[r][k] for r in range(self.world) if r != self.rank]), np.uint8)
             check(self.lib.eals_ipc_attach(self.h, which, self.world - 1, _ptr(others)))
         self.peer_store = True
+
+    def _replicas_written(self):
+        """Every whole-replica overwrite (factor init, setUV, checkpoint load) ends here when the sweep
+        kernels of OTHER ranks store into this rank's replica: no rank may start a sweep — and peer-store
+        finished rows into a replica — before every rank has finished writing its own copy, or a slower
+        rank's upload lands on top of rows a faster rank already updated (silently stale factors; the
+        1-in-5 deviating 8-GPU run of round 1)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            self.sync()
+            dist.barrier(group=self.group)
 
     def _device_matrix(self, sm: SparseMat) -> SparseMat:
         """Several ranks, matrix in host memory: every rank needs the FULL index arrays on its GPU (its
@@ -346,6 +364,33 @@ class MF_fastALS:
     def sync(self):
         check(self.lib.eals_sync(self.h))
 
+    def factor_hash(self):
+        """(hash(U), hash(V)) of this rank's replicas, computed on the device."""
+        out = np.zeros(2, np.uint64)
+        check(self.lib.eals_factor_hash(self.h, _ptr(out)))
+        return int(out[0]), int(out[1])
+
+    def replicas_consistent(self) -> bool:
+        """True when the U and V replicas of ALL ranks are bit-identical (trivially true on one rank)."""
+        if self.world == 1:
+            return True
+        import torch
+        import torch.distributed as dist
+        hu, hv = self.factor_hash()
+        # two int64 words per hash halves (all_reduce MIN/MAX on signed ints: compare 32-bit pieces)
+        parts = [hu & 0xffffffff, hu >> 32, hv & 0xffffffff, hv >> 32]
+        lo = torch.tensor(parts, dtype=torch.int64, device=f"cuda:{self.device}")
+        hi = lo.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(torch.equal(lo, hi))
+
+    def _check_replicas(self, what):
+        if self.world > 1 and os.environ.get("EALS_CHECK_REPLICAS") == "1":
+            self._half_epochs = getattr(self, "_half_epochs", 0) + 1
+            if not self.replicas_consistent():
+                raise RuntimeError(f"rank {self.rank}: replicas diverged after half-epoch {self._half_epochs} ({what})")
+
     # ---- public members of the reference (MF_fastALS.h:31-46) as host copies ------------------------
     def _get_factors(self, want_u, want_v):
         U = np.empty((self.userCount, self.factors)) if want_u else None
@@ -394,7 +439,32 @@ class MF_fastALS:
             space = _lib.EALS_HOST
         else:
             space = _lib.EALS_DEVICE
+        if self.world > 1:       # no peer may still be storing rows of an unfinished sweep into this replica
+            import torch.distributed as dist
+            self.sync()
+            dist.barrier(group=self.group)
         check(self.lib.eals_set_factors(self.h, space, _ptr(U), _ptr(V)))
+        self._replicas_written()
+
+    # ---- factor checkpoint ---------------------------------------------------------
+    def save(self, path):
+        """U, V and Wi to a binary file (format: include/eals_b200.h, eals_save_factors).  Every rank holds
+        complete replicas, so with several ranks only rank 0 writes."""
+        if self.rank == 0:
+            check(self.lib.eals_save_factors(self.h, os.fsencode(path)))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+
+    def load(self, path):
+        """Replace U, V, Wi by a checkpoint written by ``save`` (same shape and K) and rebuild the S caches;
+        buildModel / update_user / update_item then resume from that state."""
+        if self.world > 1:
+            import torch.distributed as dist
+            self.sync()
+            dist.barrier(group=self.group)
+        check(self.lib.eals_load_factors(self.h, os.fsencode(path)))
+        self._replicas_written()
 
     def refresh_S(self):
         """initS (MF_fastALS.cpp:583-595): rebuild both S caches from the current factors."""
@@ -440,6 +510,7 @@ class MF_fastALS:
         check(self.lib.eals_gram_users(self.h))
         if self.world > 1:
             allreduce_sum(self.device_tensor(_lib.BUF_SU), self.group)
+            self._check_replicas("update_user")
 
     def update_item(self):
         """Item sweep + SV refresh (MF_fastALS.cpp:146-152)."""
@@ -449,6 +520,7 @@ class MF_fastALS:
         check(self.lib.eals_gram_items(self.h))
         if self.world > 1:
             allreduce_sum(self.device_tensor(_lib.BUF_SV), self.group)
+            self._check_replicas("update_item")
 
     def update_user_thread(self, u):
         check(self.lib.eals_update_user_row(self.h, int(u)))

@@ -137,6 +137,14 @@ int eals_get_factors(eals_model* m, int32_t space, double* U, double* V);
  * update_item_SV callers and the online updateModel (MF_fastALS.cpp:223-242) need per step. */
 int eals_get_factor_row(eals_model* m, int32_t which, int32_t row, double* out);
 
+/* Factor checkpoint (the reference has only the broken setUV, MF_fastALS.cpp:106-110):
+ * U, V and Wi to / from a binary file (header: magic "EALSB200", version, factors, n_users, n_items; then
+ * U [n_users][factors], V [n_items][factors], Wi [n_items], little-endian fp64).  load checks the shape,
+ * replaces the factors and weights and rebuilds both S caches (initS); training then resumes as if the
+ * model had never been torn down. */
+int eals_save_factors(eals_model* m, const char* path);
+int eals_load_factors(eals_model* m, const char* path);
+
 /* Public member Wi (MF_fastALS.h:46). set refreshes SV. */
 int eals_set_item_weights(eals_model* m, int32_t space, const double* Wi);
 int eals_get_item_weights(eals_model* m, int32_t space, double* Wi);
@@ -168,8 +176,9 @@ int eals_patch_SU(eals_model* m, const double* old_row, const double* new_row);
 int eals_patch_SV(eals_model* m, int32_t i, const double* old_row, const double* new_row);
 
 /* MF_fastALS::loss (MF_fastALS.cpp:184-206).  terms[0] = sum over OWNED users of the per-nonzero
- * part, terms[1] = |U owned rows|^2, terms[2] = |V owned rows|^2, terms[3] = sum_u u^T SV u taken
- * as <SU, SV>_F (needs SU, SV current and complete).  loss = terms[0] + reg*(terms[1]+terms[2]) +
+ * part, terms[1] = |U owned rows|^2, terms[2] = |V owned rows|^2, terms[3] = sum_u u^T SV u over ALL
+ * users, taken as <U^T U, SV>_F: the cached SU while it is fresh, a scratch Gram of the current U after
+ * single-row user updates (which, as in the reference, leave SU stale).  loss = terms[0] + reg*(terms[1]+terms[2]) +
  * terms[3]; eals_loss forms that for a single-rank model. */
 int eals_loss_terms(eals_model* m, double terms[4]);
 int eals_loss(eals_model* m, double* loss);
@@ -196,6 +205,11 @@ int eals_stream(eals_model* m, void** cuda_stream);        /* cudaStream_t the m
  * Synchronises the old stream first. */
 int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own);
 int eals_sync(eals_model* m);
+/* 64-bit position-dependent checksums of the bit patterns of this model's U (out[0]) and V (out[1]) replicas,
+ * computed on the device.  With several ranks every replica must give the same pair after every half-epoch
+ * (the exchange is a copy; only the K x K Gram all-reduce involves arithmetic, and its result is the same
+ * on all ranks) — the multi-GPU consistency check of bench.py and tests.  Synchronises. */
+int eals_factor_hash(eals_model* m, uint64_t out[2]);
 /* Fused exchange of the updated factor rows (one process per GPU, all on one NVLink box).
  * eals_ipc_handle writes the 64-byte CUDA IPC handle of this model's U or V replica
  * (which = EALS_BUF_U / EALS_BUF_V); after the host has exchanged the handles, eals_ipc_attach maps

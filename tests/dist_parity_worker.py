@@ -35,6 +35,20 @@ def main():
     fals = MF_fastALS(sm, gt, factors=K, showLoss=False, device=local)
     assert fals.world == dist.get_world_size() and fals.world > 1
     port = PortModel(M, N, row_ptr, col_idx, factors=K)
+    # Start-up race (round-1 advisor finding): the last rank is LATE with its whole-replica overwrite while
+    # the others are already past theirs.  Without the barrier that ends setUV the early ranks' first sweep
+    # peer-stores finished rows into the late rank's replica and its upload then lands on top of them.
+    import time
+    U0, V0 = port.U * 1.25, port.V * 0.75
+    port.U[:], port.V[:] = U0, V0
+    port.init_S()
+    if rank == fals.world - 1:
+        time.sleep(1.0)
+    fals.setUV(U0, V0)
+    fals.update_user(); port.update_user()
+    fals.update_item(); port.update_item()
+    assert fals.replicas_consistent(), rank
+    assert np.abs(fals.U - port.U).max() < 1e-10 and np.abs(fals.V - port.V).max() < 1e-10, rank
     for it in range(3):
         fals.update_user(); port.update_user()
         fals.update_item(); port.update_item()
@@ -64,6 +78,7 @@ def main():
     assert np.abs(fals.U - port.U).max() < 1e-10, rank        # every replica is complete
     assert np.abs(fals.V - port.V).max() < 1e-10, rank
     assert np.abs(fals.SU - port.SU).max() <= 1e-11 * np.abs(port.SU).max()
+    assert fals.replicas_consistent(), rank
     res = fals.evaluate()
     want = port.evaluate(gt, 10, compat=True)[0]
     assert np.allclose(res, want, rtol=0, atol=1e-12), (res, want)

@@ -23,7 +23,7 @@ def test_sharded_training_matches_oracle(world, peer_store):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, EALS_PEER_STORE="0" if peer_store == "0" else "1",
-               EALS_PEER_PRED_CACHE="1" if peer_store == "pc" else "0")
+               EALS_PEER_PRED_CACHE="1" if peer_store == "pc" else "0", EALS_CHECK_REPLICAS="1")
     peer_store, port = ("1", 20) if peer_store == "pc" else (peer_store, 10 * int(peer_store))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world + port),

@@ -366,3 +366,127 @@ def test_errors_are_reported_not_swallowed():
     sm.col_idx = col_idx                             # keep the bad order
     with pytest.raises(EalsError):
         MF_fastALS(sm, None, factors=8)
+
+
+@pytest.mark.parametrize("K", [129, 200, 256])
+def test_factors_above_128_all_kernel_families(K):
+    """K in 129..256 takes its own code paths (LD = 256: S cache read from global memory in the warp
+    kernels, two block pairs in the Gram): short, mid and heavy rows, S caches, loss and evaluation."""
+    lens = [1, 5, 31, 32, 33, 64, 100, 128, 129, 200, 256, 300, 384, 512, 513, 900]
+    M, N = len(lens) * 4, 1000
+    rng = np.random.default_rng(K)
+    row_ptr, cols = [0], []
+    for u in range(M):
+        n = lens[u % len(lens)]
+        c = set(rng.choice(N, size=n, replace=False).tolist())
+        c.add(7)                                   # column 7 is rated by everybody -> item-side rows differ in length too
+        if u % 2:
+            c.add(11)
+        cols.append(np.array(sorted(c), np.int32))
+        row_ptr.append(row_ptr[-1] + len(c))
+    row_ptr, col_idx = np.asarray(row_ptr, np.int64), np.concatenate(cols)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    assert np.array_equal(fals.U, port.U) and np.array_equal(fals.V, port.V)
+    for got, want in ((fals.SU, port.SU), (fals.SV, port.SV)):
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    for it in range(2):
+        fals.update_user(); port.update_user()
+        assert np.abs(fals.U - port.U).max() < 1e-10, it
+        fals.update_item(); port.update_item()
+        assert np.abs(fals.V - port.V).max() < 1e-10, it
+        lg, lc = fals.loss(), port.loss()
+        assert abs(lg - lc) <= 1e-10 * abs(lc), (it, lg, lc)
+    assert np.abs(fals.SU - port.SU).max() <= 1e-11 * np.abs(port.SU).max()
+    assert np.abs(fals.SV - port.SV).max() <= 1e-11 * np.abs(port.SV).max()
+    gt = rng.integers(0, N, size=M).astype(np.int32)
+    for compat in (True, False):
+        want_mean, whr, wndcg, wprec, wcnt = port.evaluate(gt, 10, compat=compat)
+        got_mean, hr, ndcg, prec, cnt = fals.evaluate(gt, 10, exact=not compat, per_user=True)
+        assert np.array_equal(cnt, wcnt)
+        assert np.array_equal(hr, whr) and np.array_equal(ndcg, wndcg) and np.array_equal(prec, wprec)
+
+
+def test_loss_with_a_stale_SU_cache_follows_the_reference():
+    """update_user_thread leaves SU alone (MF_fastALS.cpp:243-322); the reference's loss() takes
+    sum_u u^T SV u from U itself (:199-200), so it stays right while SU is stale.  Ours must too."""
+    M, N, K = 180, 140, 16
+    row_ptr, col_idx = random_csr(M, N, 9, seed=31)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    fals.update_user(); port.update_user()
+    fals.update_item(); port.update_item()
+    su_before = fals.SU
+    for u in (3, 77, 120):
+        fals.update_user_thread(u)                 # no update_user_SU
+        port.update_user(u, u + 1)
+    assert np.array_equal(fals.SU, su_before)      # our SU is stale, like the reference's
+    lg, lc = fals.loss(), port.loss()              # the oracle's loss never reads SU
+    assert abs(lg - lc) <= 1e-10 * abs(lc), (lg, lc)
+    assert np.array_equal(fals.SU, su_before)      # ... and loss() did not refresh it behind the caller's back
+    fals.updateModel(9, 33, patch_S=False)         # the reference's stale-cache arithmetic end to end
+    import io
+    fals.out = io.StringIO()
+    got = fals.showLoss(0, 0.0, float("inf"))
+    from eals_cpp_b200.model import MF_fastALS, SparseMat   # fresh model on the grown matrix = ground truth
+    chk = MF_fastALS(fals.trainMatrix, None, factors=K, showLoss=False, init=False)
+    chk.setUV(fals.U, fals.V)
+    chk.Wi = fals.Wi
+    want = chk.loss()
+    assert abs(got - want) <= 1e-10 * abs(want)
+
+
+def test_checkpoint_save_load_resume(tmp_path):
+    """save / load of U, V, Wi: a model rebuilt from the checkpoint resumes training on
+    the interrupted run's trajectory."""
+    from eals_cpp_b200._lib import EalsError
+    M, N, K = 400, 260, 20
+    row_ptr, col_idx = random_csr(M, N, 11, seed=77, empty_frac=0.04)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+    w = fals.Wi
+    w[5] *= 1.5                                    # a non-default weight must survive the round trip
+    fals.Wi = w; port.Wi[:] = w; port.init_S()
+    path = str(tmp_path / "factors.eals")
+    fals.save(path)
+    U2, V2 = fals.U, fals.V
+    fals.close()
+    from eals_cpp_b200.model import MF_fastALS, SparseMat
+    again = MF_fastALS(SparseMat.from_csr(M, N, row_ptr, col_idx), None, factors=K, showLoss=False, init=False)
+    again.load(path)
+    assert np.array_equal(again.U, U2) and np.array_equal(again.V, V2) and np.array_equal(again.Wi, w)
+    for _ in range(2):
+        again.update_user(); port.update_user()
+        again.update_item(); port.update_item()
+    assert np.abs(again.U - port.U).max() < 1e-10 and np.abs(again.V - port.V).max() < 1e-10
+    lg, lc = again.loss(), port.loss()
+    assert abs(lg - lc) <= 1e-10 * abs(lc)
+    other = MF_fastALS(SparseMat.from_csr(M, N, row_ptr, col_idx), None, factors=K + 4, showLoss=False, init=False)
+    with pytest.raises(EalsError):
+        other.load(path)                           # wrong K
+    with pytest.raises(EalsError):
+        other.load(str(tmp_path / "missing.eals"))
+
+
+def test_update_model_overwrites_an_existing_rating_with_one():
+    """trainMatrix.setValue(u, i, 1) / W.setValue(u, i, w_new) (MF_fastALS.cpp:224-226) on an entry that
+    already exists: rating and weight become 1."""
+    from oracle.bindings import csr_to_csc
+    M, N, K = 120, 90, 16
+    row_ptr, col_idx = random_csr(M, N, 8, seed=13)
+    val = np.random.default_rng(3).uniform(0.5, 3.0, size=len(col_idx))
+    fals, port = _models(M, N, row_ptr, col_idx, K, val=val)
+    fals.update_user(); port.update_user(); port.SU = port.p.gram_plain(port.U)
+    fals.update_item(); port.update_item(); port.SV = port.p.gram_weighted(port.V, port.Wi)
+    u = 10
+    i = int(col_idx[row_ptr[u]])                   # an existing entry with a non-unit rating
+    assert val[row_ptr[u]] != 1.0
+    fals.updateModel(u, i)
+    val2 = val.copy(); val2[row_ptr[u]] = 1.0
+    port.val = val2
+    port.col_ptr, port.row_idx, port.cval, _ = csr_to_csc(M, N, row_ptr, col_idx, val2)
+    for _ in range(10):
+        port.update_user(u, u + 1)
+        port.update_item(i, i + 1)
+    assert np.abs(fals.U - port.U).max() < 1e-10 and np.abs(fals.V - port.V).max() < 1e-10
+    assert fals.trainMatrix.row_val[row_ptr[u]] == 1.0
