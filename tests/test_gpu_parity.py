@@ -426,11 +426,10 @@ def test_loss_with_a_stale_SU_cache_follows_the_reference():
     import io
     fals.out = io.StringIO()
     got = fals.showLoss(0, 0.0, float("inf"))
-    from eals_cpp_b200.model import MF_fastALS, SparseMat   # fresh model on the grown matrix = ground truth
-    chk = MF_fastALS(fals.trainMatrix, None, factors=K, showLoss=False, init=False)
-    chk.setUV(fals.U, fals.V)
-    chk.Wi = fals.Wi
-    want = chk.loss()
+    # ground truth: the reference's formula on the grown matrix with the model's own (stale) SV — :193-200
+    tm = fals.trainMatrix
+    want = port.p.loss(np.ascontiguousarray(tm.row_ptr, np.int64), np.ascontiguousarray(tm.col_idx, np.int32), None,
+                       fals.U, fals.V, fals.SV, fals.Wi, 0.01)
     assert abs(got - want) <= 1e-10 * abs(want)
 
 
