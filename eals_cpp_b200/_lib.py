@@ -72,6 +72,7 @@ SIGNATURES = {
     "eals_predict": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "eals_evaluate": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "eals_evaluate_user": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "eals_eval_stats": (C.c_int, [_P, _P]),
     "eals_leading_dim": (C.c_int, [_P]),
     "eals_device_buffer": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "eals_stream": (C.c_int, [_P, C.POINTER(_P)]),

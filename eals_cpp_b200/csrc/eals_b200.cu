@@ -20,12 +20,18 @@
 #include <utility>
 #include <vector>
 
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "cd_block.cuh"
 #include "cd_sweep.cuh"
 #include "common.cuh"
 #include "eval.cuh"
+#include "eval_tc.cuh"
 #include "gram.cuh"
 #include "loss.cuh"
 
@@ -187,6 +193,9 @@ struct eals_model {
   double acc_ms[T_COUNT] = {0};
   int64_t acc_calls[T_COUNT] = {0};
   bool factors_set = false;
+  struct eals_eval_ws* eval = nullptr;   // evaluation workspace (grow-only)
+  int eval_engine = 0;                   // engine of the last evaluate: 0 exact fp64 tiles, 1 tcgen05 filter + exact re-score
+  long long eval_candidates = 0, eval_pairs = 0;
   bool su_fresh = true;          // SU describes the current U (false after single-row user updates without a Gram)
   double* S_tmp = nullptr;       // [LD][LD] scratch Gram for loss() while SU is stale
   int* flags = nullptr;          // [8] device scratch for validation kernels (no malloc/free per call)
@@ -1178,35 +1187,65 @@ int reference_rank(const std::vector<std::pair<int, int>>& nz, int n_items, int 
   return -1;
 }
 
-int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int32_t* gt_slot_h, int topk,
-                   int mode, double sums[3], double* hr, double* ndcg, double* prec, int32_t* count_larger) {
-  const int n = (int)users_h.size();
-  sums[0] = sums[1] = sums[2] = 0;
-  if (n == 0) return EALS_OK;
+// Grow-only device workspace of the evaluation (kept across calls: no cudaMalloc / cudaFree per evaluate).
+template <typename T>
+struct WsBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) { return dev_reserve(&p, &cap, n); }
+  void release() { cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct eals_eval_ws {
+  WsBuf<int32_t> users, gt, cnt, cnt_exact, list_a, list_b, perm, ids, exps, scalars;
+  WsBuf<double> gts;
+  WsBuf<__half> Uh, Vh, W;
+  WsBuf<float> un_hat, un_del, un_h, vn_hat, vn_del, vn_h;
+  WsBuf<float4> sp0, sp1;
+  WsBuf<float2> tile_norm;
+  WsBuf<uint32_t> keys, keys_out;
+  WsBuf<uint8_t> flags;
+  WsBuf<unsigned char> cub_tmp;
+  WsBuf<unsigned long long> counters;   // [0] max |V| bits, [1] pairs, [2] triples
+  WsBuf<eals::tc::EvalPair> pairs;
+  WsBuf<eals::EvalTriple> triples;
+  WsBuf<int32_t> active;
+  void release() {
+    users.release(); gt.release(); cnt.release(); cnt_exact.release(); list_a.release(); list_b.release(); perm.release();
+    ids.release(); exps.release(); scalars.release(); gts.release(); Uh.release(); Vh.release(); W.release();
+    un_hat.release(); un_del.release(); un_h.release(); vn_hat.release(); vn_del.release(); vn_h.release();
+    sp0.release(); sp1.release(); tile_norm.release(); keys.release(); keys_out.release(); flags.release();
+    cub_tmp.release(); counters.release(); pairs.release(); triples.release(); active.release();
+  }
+};
+
+namespace {
+
+eals_eval_ws& eval_ws(eals_model* m) {
+  if (!m->eval) m->eval = new eals_eval_ws();
+  return *m->eval;
+}
+
+// ---- scan engine 1: exact fp64 tiles (eval.cuh), item chunks with an early-out of decided users --------
+// Used for short user lists (evaluate_for_user), as the engine the tensor filter is tested against
+// (EALS_EVAL_SCALAR=1) and as its fall-back when the candidate list overflows.
+int scan_exact(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples,
+               std::vector<int32_t>& cnt, std::vector<eals::EvalTriple>& tr) {
+  eals_eval_ws& ws = eval_ws(m);
   const int K = m->K, LD = m->LD, N = m->N;
-  int32_t *d_users = nullptr, *d_count = nullptr, *gt_dev = nullptr;
-  double* d_gts = nullptr;
-  OK(dev_alloc(&d_users, (size_t)n));
-  OK(dev_alloc(&gt_dev, (size_t)n));
-  CU(cudaMemcpyAsync(gt_dev, gt_slot_h, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
-  OK(dev_alloc(&d_count, (size_t)n));
-  OK(dev_alloc(&d_gts, (size_t)n));
-  CU(cudaMemcpyAsync(d_users, users_h.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
+  OK(ws.cnt.reserve((size_t)n));
+  OK(ws.active.reserve((size_t)n));
+  int32_t *d_count = ws.cnt.p, *d_active = ws.active.p;
   CU(cudaMemsetAsync(d_count, 0, sizeof(int32_t) * n, m->stream));
-  eals::eval_gt_score_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->U, m->V, gt_dev, d_users, 0, n, K, LD, d_gts);
-  OK(check_launch(m));
   const int item_tiles = (N + eals::kEvalTile - 1) / eals::kEvalTile;
   // Count strictly larger scores chunk by chunk of items.  The reference gives (0,0,0) as soon as the
   // count exceeds topK (MF_fastALS.cpp:633-634) and the total does not depend on the scan order, so a
-  // user whose count already exceeds topK after a chunk is decided and leaves the active list; only
-  // the users still in the race (the eventual hits and near-hits) are scored against the whole
-  // catalogue.  Chunks grow geometrically: 4096, 16384, ... items.
-  std::vector<int32_t> cnt((size_t)n, 0);
+  // user whose count already exceeds topK after a chunk is decided and leaves the active list.
   {
     std::vector<int32_t> active((size_t)n);
     for (int s = 0; s < n; s++) active[s] = s;
-    int32_t* d_active = nullptr;
-    OK(dev_alloc(&d_active, (size_t)n));
     std::vector<int32_t> cnt_a;
     int64_t chunk = 4096;
     if (const char* e = getenv("EALS_EVAL_FIRST_CHUNK")) chunk = std::max<int64_t>(64, atoll(e));
@@ -1216,8 +1255,7 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
       CU(cudaMemcpyAsync(d_active, active.data(), sizeof(int32_t) * na, cudaMemcpyHostToDevice, m->stream));
       const long long utiles = (na + eals::kEvalTile - 1) / eals::kEvalTile;
       const long long itiles = (i1 - (int)i0 + eals::kEvalTile - 1) / eals::kEvalTile;
-      // keep each launch below the grid limit: split the active list if needed
-      const long long max_ut = std::max<long long>(1, 0x7fffffffLL / itiles);
+      const long long max_ut = std::max<long long>(1, 0x7fffffffLL / itiles);   // grid limit
       for (long long ut0 = 0; ut0 < utiles; ut0 += max_ut) {
         const long long ut1 = std::min(utiles, ut0 + max_ut);
         const int a0 = (int)(ut0 * eals::kEvalTile), a1 = (int)std::min<long long>(na, ut1 * eals::kEvalTile);
@@ -1225,10 +1263,10 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
             m->U, m->V, d_users, d_active + a0, 0, a1 - a0, (int)i0, i1, K, LD, d_gts, d_count, nullptr, nullptr, 0);
         OK(check_launch(m));
       }
-      if (na == n) {   // first round: everything
+      if (na == n) {
         CU(cudaMemcpyAsync(cnt.data(), d_count, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, m->stream));
         CU(cudaStreamSynchronize(m->stream));
-      } else {         // later rounds: the (few) active slots only
+      } else {
         OK(ensure_partials(m, (size_t)(na + 1) / 2 + 1));
         int32_t* d_tmp = reinterpret_cast<int32_t*>(m->partials);
         eals::gather_i32_kernel<<<(na + 255) / 256, 256, 0, m->stream>>>(d_count, d_active, na, d_tmp);
@@ -1243,68 +1281,288 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
         if (cnt[active[a]] <= topk) active[keep++] = active[a];
       active.resize(keep);
     }
-    cudaFree(d_active);
   }
+  if (!want_triples) return EALS_OK;
+  // survivors of the early-out: the (item, (int)score) pairs with a non-zero key
+  std::vector<int32_t> surv;
+  for (int s = 0; s < n; s++)
+    if (cnt[s] <= topk) surv.push_back(s);
+  const int ns = (int)surv.size();
+  if (ns == 0) return EALS_OK;
+  CU(cudaMemcpyAsync(d_active, surv.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, m->stream));
+  OK(ws.counters.reserve(4));
+  unsigned long long* d_nt = ws.counters.p + 2;
+  unsigned long long cap = 1ull << 20, got = 0;
+  const long long utiles = (ns + eals::kEvalTile - 1) / eals::kEvalTile;
+  const long long max_ut = std::max<long long>(1, 0x7fffffffLL / item_tiles);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    OK(ws.triples.reserve((size_t)cap));
+    CU(cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), m->stream));
+    for (long long ut0 = 0; ut0 < utiles; ut0 += max_ut) {
+      const long long ut1 = std::min(utiles, ut0 + max_ut);
+      const int a0 = (int)(ut0 * eals::kEvalTile), a1 = (int)std::min<long long>(ns, ut1 * eals::kEvalTile);
+      eals::eval_tile_kernel<1><<<(unsigned)((ut1 - ut0) * item_tiles), eals::kEvalThreads, 0, m->stream>>>(
+          m->U, m->V, d_users, d_active + a0, 0, a1 - a0, 0, N, K, LD, nullptr, nullptr, ws.triples.p, d_nt, cap);
+      OK(check_launch(m));
+    }
+    CU(cudaMemcpyAsync(&got, d_nt, sizeof(got), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    if (got <= cap) break;
+    cap = got;  // exact size known now: the second pass cannot overflow
+  }
+  tr.resize((size_t)got);
+  if (got) CU(cudaMemcpy(tr.data(), ws.triples.p, sizeof(eals::EvalTriple) * got, cudaMemcpyDeviceToHost));
+  return EALS_OK;
+}
+
+// ---- scan engine 2: tcgen05 filter + exact re-score of the candidates (eval_tc.cuh) ---------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_half_map(CUtensorMap* map, const __half* base, size_t rows, int KP) {
+  static TensorMapEncodeFn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &q) != cudaSuccess || !encode)
+      return fail(EALS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)KP, (cuuint64_t)std::max<size_t>(rows, 1)};
+  const cuuint64_t gstr[1] = {(cuuint64_t)KP * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)eals::tc::kKC, (cuuint32_t)eals::tc::kTM}, estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EALS_ERR_CUDA, "cuTensorMapEncodeTiled -> %d", (int)r);
+  return EALS_OK;
+}
+
+template <int NKC, int MODE>
+int launch_filter(eals_model* m, const CUtensorMap& mapU, const CUtensorMap& mapV, const eals::tc::TcArgs& a, int max_works) {
+  using C = eals::tc::Cfg<NKC>;
+  auto kern = eals::tc::eval_filter_kernel<NKC, MODE>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+  const int grid = std::max(1, std::min(m->sm_count, max_works));
+  kern<<<grid, eals::tc::kThreads, C::kSmem, m->stream>>>(mapU, mapV, a);
+  return check_launch(m);
+}
+template <int MODE>
+int launch_filter_k(eals_model* m, int nkc, const CUtensorMap& mapU, const CUtensorMap& mapV, const eals::tc::TcArgs& a, int max_works) {
+  switch (nkc) {
+    case 1: return launch_filter<1, MODE>(m, mapU, mapV, a, max_works);
+    case 2: return launch_filter<2, MODE>(m, mapU, mapV, a, max_works);
+    case 3: return launch_filter<3, MODE>(m, mapU, mapV, a, max_works);
+    case 4: return launch_filter<4, MODE>(m, mapU, mapV, a, max_works);
+  }
+  return fail(EALS_ERR_UNSUPPORTED, "factors %d in the tensor-core evaluation", nkc * 64);
+}
+
+// survivors' triples out of the re-scored candidate pairs
+__global__ void pairs_to_triples_kernel(const eals::tc::EvalPair* __restrict__ pairs, const unsigned long long* __restrict__ n_pairs,
+                                        const int32_t* __restrict__ cnt_hi, const int32_t* __restrict__ cnt_exact, int topk,
+                                        eals::EvalTriple* __restrict__ out, unsigned long long* __restrict__ n_out) {
+  const unsigned long long n = *n_pairs;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
+    const eals::tc::EvalPair pr = pairs[t];
+    if (pr.key != 0 && cnt_hi[pr.slot] <= topk && cnt_exact[pr.slot] <= topk) out[atomicAdd(n_out, 1ull)] = eals::EvalTriple{pr.slot, pr.item, pr.key};
+  }
+}
+
+__global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
+
+struct TcStats { long long candidates = 0, pairs = 0, blocks = 0; };
+
+int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples,
+            std::vector<int32_t>& cnt, std::vector<eals::EvalTriple>& tr, bool* overflow) {
+  namespace tc = eals::tc;
+  eals_eval_ws& ws = eval_ws(m);
+  *overflow = false;
+  const int K = m->K, LD = m->LD, N = m->N;
+  const int nkc = (K + tc::kKC - 1) / tc::kKC, KP = nkc * tc::kKC;
+  const int n_tiles = (N + tc::kTN - 1) / tc::kTN;
+  const int ut = nkc <= 2 ? 2 : 1;
+  cudaStream_t st = m->stream;
+  // ---- preparation: fp16 copies, norms, item order, per-slot thresholds ----
+  OK(ws.counters.reserve(4));
+  OK(ws.keys.reserve((size_t)N)); OK(ws.keys_out.reserve((size_t)N)); OK(ws.ids.reserve((size_t)N)); OK(ws.perm.reserve((size_t)N));
+  OK(ws.Vh.reserve((size_t)N * KP)); OK(ws.vn_hat.reserve((size_t)N)); OK(ws.vn_del.reserve((size_t)N)); OK(ws.vn_h.reserve((size_t)N));
+  OK(ws.tile_norm.reserve((size_t)n_tiles));
+  OK(ws.Uh.reserve((size_t)n * KP)); OK(ws.W.reserve(((size_t)n + 2 * tc::kTM) * KP));
+  OK(ws.un_hat.reserve((size_t)n)); OK(ws.un_del.reserve((size_t)n)); OK(ws.un_h.reserve((size_t)n)); OK(ws.exps.reserve((size_t)n));
+  OK(ws.sp0.reserve((size_t)n)); OK(ws.sp1.reserve((size_t)n));
+  OK(ws.cnt.reserve((size_t)n)); OK(ws.cnt_exact.reserve((size_t)n));
+  OK(ws.list_a.reserve((size_t)n)); OK(ws.list_b.reserve((size_t)n)); OK(ws.flags.reserve((size_t)n));
+  OK(ws.scalars.reserve(8));
+  size_t tmp_sort = 0, tmp_sel = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, ws.keys.p, ws.keys_out.p, ws.ids.p, ws.perm.p, N, 0, 32, st);
+  {
+    size_t t2 = 0;
+    cub::DeviceSelect::Flagged(nullptr, tmp_sel, ws.list_a.p, ws.flags.p, ws.list_b.p, ws.scalars.p, n, st);
+    cub::DeviceSelect::Flagged(nullptr, t2, thrust::counting_iterator<int32_t>(0), ws.flags.p, ws.list_b.p, ws.scalars.p, n, st);
+    tmp_sel = std::max(tmp_sel, t2);
+  }
+  OK(ws.cub_tmp.reserve(std::max(tmp_sort, tmp_sel) + 16));
+  unsigned long long* d_vmax = ws.counters.p;
+  CU(cudaMemsetAsync(ws.counters.p, 0, 4 * sizeof(unsigned long long), st));
+  tc::absmax_kernel<<<4 * m->sm_count, 256, 0, st>>>(m->V, (size_t)N, K, LD, d_vmax);
+  OK(check_launch(m));
+  tc::item_sort_keys_kernel<<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, st>>>(m->V, K, LD, N, ws.keys.p, ws.ids.p);
+  OK(check_launch(m));
+  if (cub::DeviceRadixSort::SortPairs(ws.cub_tmp.p, tmp_sort, ws.keys.p, ws.keys_out.p, ws.ids.p, ws.perm.p, N, 0, 32, st) != cudaSuccess)
+    return fail(EALS_ERR_CUDA, "item norm sort");
+  m->launches++;
+  {
+    tc::PrepOut o{ws.Vh.p, ws.vn_hat.p, ws.vn_del.p, ws.vn_h.p, nullptr};
+    tc::prep_rows_kernel<false><<<(unsigned)(((size_t)N * 32 + 255) / 256), 256, 0, st>>>(m->V, K, LD, KP, N, ws.perm.p, 0, d_vmax, o);
+    OK(check_launch(m));
+    tc::tile_norm_kernel<<<n_tiles, 32, 0, st>>>(ws.vn_h.p, ws.vn_del.p, N, n_tiles, ws.tile_norm.p);
+    OK(check_launch(m));
+  }
+  {
+    tc::PrepOut o{ws.Uh.p, ws.un_hat.p, ws.un_del.p, ws.un_h.p, ws.exps.p};
+    tc::prep_rows_kernel<true><<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(m->U, K, LD, KP, n, d_users, 0, d_vmax, o);
+    OK(check_launch(m));
+    const double gamma = (double)KP * (1.0 / 2097152.0);   // KP * 2^-21
+    tc::slot_params_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_gts, ws.exps.p, d_vmax, ws.un_hat.p, ws.un_del.p, ws.un_h.p, n, gamma, ws.sp0.p, ws.sp1.p);
+    OK(check_launch(m));
+  }
+  CU(cudaMemsetAsync(ws.cnt.p, 0, sizeof(int32_t) * n, st));
+  CU(cudaMemsetAsync(ws.cnt_exact.p, 0, sizeof(int32_t) * n, st));
+  CUtensorMap mapV, mapU0, mapW;
+  OK(make_half_map(&mapV, ws.Vh.p, (size_t)N, KP));
+  OK(make_half_map(&mapU0, ws.Uh.p, (size_t)n, KP));
+  OK(make_half_map(&mapW, ws.W.p, (size_t)n + 2 * tc::kTM, KP));
+  int32_t* d_n = ws.scalars.p;          // [0]: size of the current working list, [1]: next
+  set_i32_kernel<<<1, 1, 0, st>>>(d_n, n);
+  OK(check_launch(m));
+
+  // ---- MODE 0 over L2-sized item blocks, working set compacted on the device between them ----
+  tc::TcArgs a{};
+  a.sp0 = ws.sp0.p; a.sp1 = ws.sp1.p; a.tile_norm = ws.tile_norm.p; a.n_items = N; a.cnt_hi = ws.cnt.p; a.perm = ws.perm.p;
+  int64_t blk = 32768;
+  if (const char* e = getenv("EALS_EVAL_FIRST_CHUNK")) blk = std::max<int64_t>(tc::kTN, atoll(e));
+  const int32_t* list = nullptr;        // identity
+  int32_t *list_next = ws.list_a.p, *list_other = ws.list_b.p;
+  const int max_works = (n + ut * tc::kTM - 1) / (ut * tc::kTM);
+  auto compact = [&](void) -> int {     // undecided users of the current list -> list_next, their rows -> W
+    tc::undecided_flags_kernel<<<(n + 255) / 256, 256, 0, st>>>(list, d_n, n, ws.cnt.p, topk, ws.flags.p);
+    OK(check_launch(m));
+    cudaError_t e;
+    if (list) e = cub::DeviceSelect::Flagged(ws.cub_tmp.p, tmp_sel, list, ws.flags.p, list_next, d_n + 1, n, st);
+    else e = cub::DeviceSelect::Flagged(ws.cub_tmp.p, tmp_sel, thrust::counting_iterator<int32_t>(0), ws.flags.p, list_next, d_n + 1, n, st);
+    if (e != cudaSuccess) return fail(EALS_ERR_CUDA, "working-set compaction");
+    m->launches++;
+    CU(cudaMemcpyAsync(d_n, d_n + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    tc::gather_rows_kernel<<<8 * m->sm_count, 256, 0, st>>>(ws.Uh.p, KP, list_next, d_n, ws.W.p);
+    OK(check_launch(m));
+    list = list_next;
+    std::swap(list_next, list_other);
+    return EALS_OK;
+  };
+  for (int64_t i0 = 0; i0 < N; ) {
+    const int64_t i1 = std::min<int64_t>(N, i0 + blk);
+    a.act = list; a.n_act = d_n;
+    a.it0 = (int)(i0 / tc::kTN); a.it1 = (int)((i1 + tc::kTN - 1) / tc::kTN);
+    OK(launch_filter_k<0>(m, nkc, list ? mapW : mapU0, mapV, a, max_works));
+    OK(compact());
+    i0 = (int64_t)a.it1 * tc::kTN;
+    blk = std::min<int64_t>(blk * 4, 262144);
+  }
+  // ---- MODE 1 for the candidates (certain count <= topK): emit, re-score exactly ----
+  int n_cand = 0;
+  CU(cudaMemcpyAsync(&n_cand, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  unsigned long long got = 0;
+  unsigned long long* d_np = ws.counters.p + 1;
+  if (n_cand > 0) {
+    unsigned long long cap = std::min<unsigned long long>(1ull << 27, std::max<unsigned long long>(1ull << 20, 512ull * (unsigned long long)n_cand));
+    if (const char* e = getenv("EALS_EVAL_PAIR_CAP")) cap = std::max<unsigned long long>(16, strtoull(e, nullptr, 10));
+    unsigned long long hard_cap = 1ull << 30;           // 16 GB of pairs: beyond this the filter is not filtering
+    if (const char* e = getenv("EALS_EVAL_PAIR_HARD_CAP")) hard_cap = strtoull(e, nullptr, 10);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      OK(ws.pairs.reserve((size_t)cap));
+      CU(cudaMemsetAsync(d_np, 0, sizeof(unsigned long long), st));
+      a.act = list; a.n_act = d_n; a.it0 = 0; a.it1 = n_tiles;
+      a.pairs = ws.pairs.p; a.n_pairs = d_np; a.cap_pairs = cap;
+      OK(launch_filter_k<1>(m, nkc, mapW, mapV, a, (n_cand + ut * tc::kTM - 1) / (ut * tc::kTM)));
+      CU(cudaMemcpyAsync(&got, d_np, sizeof(got), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (got <= cap) break;
+      if (attempt == 1 || got > hard_cap) { *overflow = true; return EALS_OK; }   // degenerate scores: exact engine instead
+      cap = got;
+    }
+    if (got) {
+      tc::eval_rescore_kernel<<<8 * m->sm_count, 256, 0, st>>>(m->U, m->V, K, LD, d_users, 0, d_gts, ws.pairs.p, d_np, got, ws.cnt_exact.p);
+      OK(check_launch(m));
+    }
+  }
+  std::vector<int32_t> hi((size_t)n), ex((size_t)n);
+  CU(cudaMemcpyAsync(hi.data(), ws.cnt.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ex.data(), ws.cnt_exact.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  unsigned long long n_tr = 0;
+  if (want_triples && got) {
+    OK(ws.triples.reserve((size_t)got));
+    unsigned long long* d_nt = ws.counters.p + 2;
+    pairs_to_triples_kernel<<<8 * m->sm_count, 256, 0, st>>>(ws.pairs.p, d_np, ws.cnt.p, ws.cnt_exact.p, topk, ws.triples.p, d_nt);
+    OK(check_launch(m));
+    CU(cudaMemcpyAsync(&n_tr, d_nt, sizeof(n_tr), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  for (int s = 0; s < n; s++) cnt[s] = hi[s] > topk ? topk + 1 : ex[s];
+  tr.resize((size_t)n_tr);
+  if (n_tr) CU(cudaMemcpy(tr.data(), ws.triples.p, sizeof(eals::EvalTriple) * n_tr, cudaMemcpyDeviceToHost));
+  if (getenv("EALS_VERBOSE") && getenv("EALS_VERBOSE")[0] == '1')
+    fprintf(stderr, "[eals] evaluate (tcgen05 filter): %d users, %d candidates after the certain count, %llu pairs re-scored exactly, %llu keys\n",
+            n, n_cand, got, n_tr);
+  m->eval_candidates = n_cand; m->eval_pairs = (long long)got;
+  return EALS_OK;
+}
+
+constexpr int kTcMinUsers = 128;
+
+int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int32_t* gt_slot_h, int topk,
+                   int mode, double sums[3], double* hr, double* ndcg, double* prec, int32_t* count_larger) {
+  const int n = (int)users_h.size();
+  sums[0] = sums[1] = sums[2] = 0;
+  if (n == 0) return EALS_OK;
+  eals_eval_ws& ws = eval_ws(m);
+  const int K = m->K, LD = m->LD, N = m->N;
+  OK(ws.users.reserve((size_t)n)); OK(ws.gt.reserve((size_t)n)); OK(ws.gts.reserve((size_t)n));
+  CU(cudaMemcpyAsync(ws.gt.p, gt_slot_h, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(ws.users.p, users_h.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
+  eals::eval_gt_score_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->U, m->V, ws.gt.p, ws.users.p, 0, n, K, LD, ws.gts.p);
+  OK(check_launch(m));
+  std::vector<int32_t> cnt((size_t)n, 0);
+  std::vector<eals::EvalTriple> tr;
+  const bool want_triples = mode != EALS_EVAL_EXACT;
+  const bool scalar_only = getenv("EALS_EVAL_SCALAR") && getenv("EALS_EVAL_SCALAR")[0] == '1';
+  bool done = false;
+  m->eval_engine = 0;
+  if (n >= kTcMinUsers && K <= 256 && !scalar_only) {
+    bool overflow = false;
+    OK(scan_tc(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tr, &overflow));
+    done = !overflow;
+    if (done) m->eval_engine = 1;
+  }
+  if (!done) OK(scan_exact(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tr));
 
   std::vector<int> pos((size_t)n, -1);
   if (mode == EALS_EVAL_EXACT) {
     for (int s = 0; s < n; s++)
       if (cnt[s] < topk) pos[s] = cnt[s];
   } else {
-    // survivors of the early-out (countLarger > topK -> zeros, MF_fastALS.cpp:633-634)
-    std::vector<int32_t> surv_users, surv_slot;
-    for (int s = 0; s < n; s++)
-      if (cnt[s] <= topk) { surv_users.push_back(users_h[s]); surv_slot.push_back(s); }
-    const int ns = (int)surv_users.size();
-    if (ns > 0) {
-      int32_t* d_su = nullptr;
-      unsigned long long* d_nt = nullptr;
-      eals::EvalTriple* d_tr = nullptr;
-      OK(dev_alloc(&d_su, (size_t)ns));
-      OK(dev_alloc(&d_nt, 1));
-      CU(cudaMemcpyAsync(d_su, surv_users.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, m->stream));
-      unsigned long long cap = 1ull << 20, got = 0;
-      // survivor tiles per launch bounded by the grid limit; `active` = identity so that the slot a
-      // sub-launch reports is the absolute survivor index
-      int32_t* d_iota = nullptr;
-      {
-        std::vector<int32_t> iota((size_t)ns);
-        for (int t = 0; t < ns; t++) iota[t] = t;
-        OK(dev_alloc(&d_iota, (size_t)ns));
-        CU(cudaMemcpyAsync(d_iota, iota.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, m->stream));
-        CU(cudaStreamSynchronize(m->stream));
-      }
-      const long long utiles = (ns + eals::kEvalTile - 1) / eals::kEvalTile;
-      const long long max_ut = std::max<long long>(1, 0x7fffffffLL / item_tiles);
-      for (int attempt = 0; attempt < 2; attempt++) {
-        cudaFree(d_tr);
-        OK(dev_alloc(&d_tr, (size_t)cap));
-        CU(cudaMemsetAsync(d_nt, 0, sizeof(unsigned long long), m->stream));
-        for (long long ut0 = 0; ut0 < utiles; ut0 += max_ut) {
-          const long long ut1 = std::min(utiles, ut0 + max_ut);
-          const int a0 = (int)(ut0 * eals::kEvalTile), a1 = (int)std::min<long long>(ns, ut1 * eals::kEvalTile);
-          eals::eval_tile_kernel<1><<<(unsigned)((ut1 - ut0) * item_tiles), eals::kEvalThreads, 0, m->stream>>>(
-              m->U, m->V, d_su, d_iota + a0, 0, a1 - a0, 0, N, K, LD, nullptr, nullptr, d_tr, d_nt, cap);
-          OK(check_launch(m));
-        }
-        CU(cudaMemcpyAsync(&got, d_nt, sizeof(got), cudaMemcpyDeviceToHost, m->stream));
-        CU(cudaStreamSynchronize(m->stream));
-        if (got <= cap) break;
-        cap = got;  // exact size known now: second pass cannot overflow
-      }
-      std::vector<eals::EvalTriple> tr((size_t)got);
-      if (got) CU(cudaMemcpy(tr.data(), d_tr, sizeof(eals::EvalTriple) * got, cudaMemcpyDeviceToHost));
-      cudaFree(d_su); cudaFree(d_nt); cudaFree(d_tr); cudaFree(d_iota);
-      std::sort(tr.begin(), tr.end(), [](const eals::EvalTriple& a, const eals::EvalTriple& b) {
-        return a.slot != b.slot ? a.slot < b.slot : a.item < b.item;
-      });
-      size_t q = 0;
-      std::vector<std::pair<int, int>> nz;
-      for (int t = 0; t < ns; t++) {
-        nz.clear();
-        while (q < tr.size() && tr[q].slot == t) { nz.emplace_back(tr[q].item, tr[q].key); q++; }
-        pos[surv_slot[t]] = reference_rank(nz, N, topk, gt_slot_h[surv_slot[t]]);
-      }
+    // replay of the reference's ranking for the survivors of the early-out (countLarger > topK -> zeros,
+    // MF_fastALS.cpp:633-634); triples carry the slot, the (item, key) stream of a slot ascends by item
+    std::sort(tr.begin(), tr.end(), [](const eals::EvalTriple& a, const eals::EvalTriple& b) {
+      return a.slot != b.slot ? a.slot < b.slot : a.item < b.item;
+    });
+    size_t q = 0;
+    std::vector<std::pair<int, int>> nz;
+    for (int s = 0; s < n; s++) {
+      if (cnt[s] > topk) continue;
+      nz.clear();
+      while (q < tr.size() && tr[q].slot < s) q++;
+      while (q < tr.size() && tr[q].slot == s) { nz.emplace_back(tr[q].item, tr[q].key); q++; }
+      pos[s] = reference_rank(nz, N, topk, gt_slot_h[s]);
     }
   }
   for (int s = 0; s < n; s++) {
@@ -1316,7 +1574,6 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
     if (count_larger) count_larger[s] = std::min(cnt[s], topk + 1);
     sums[0] += r0; sums[1] += r1; sums[2] += r2;
   }
-  cudaFree(d_users); cudaFree(d_count); cudaFree(d_gts); cudaFree(gt_dev);
   return EALS_OK;
 }
 
@@ -1354,6 +1611,7 @@ int eals_destroy(eals_model* m) {
   cudaFree(m->pc_stage_u); cudaFree(m->pc_stage_i);
   cudaFree(m->route_src_u); cudaFree(m->route_dst_u); cudaFree(m->route_src_i); cudaFree(m->route_dst_i);
   for (void* p : m->graveyard) cudaFree(p);
+  if (m->eval) { m->eval->release(); delete m->eval; m->eval = nullptr; }
   cudaFree(m->full_rp); cudaFree(m->full_cp); cudaFree(m->full_ci); cudaFree(m->full_ri); cudaFree(m->route_tmp);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
@@ -1745,6 +2003,12 @@ int eals_evaluate_user(eals_model* m, int32_t u, int32_t gt_item, int32_t topk, 
   CU(cudaSetDevice(m->p.device));
   std::vector<int32_t> users(1, u);
   return evaluate_slots(m, users, &gt_item, topk, mode, out, nullptr, nullptr, nullptr, nullptr);
+}
+
+int eals_eval_stats(eals_model* m, int64_t out[3]) {
+  if (!m || !out) return fail(EALS_ERR_ARG, "null argument");
+  out[0] = m->eval_engine; out[1] = m->eval_candidates; out[2] = m->eval_pairs;
+  return EALS_OK;
 }
 
 int eals_leading_dim(const eals_model* m) { return m ? m->LD : 0; }

@@ -660,6 +660,13 @@ class MF_fastALS:
             return res, hr, ndcg, prec, cnt
         return res
 
+    def eval_stats(self):
+        """Engine of the last evaluate(): 'tcgen05' (fp16 tensor-core filter + exact fp64 re-score of the close
+        calls) or 'fp64' (exact tile scan), the number of candidate users and of re-scored pairs."""
+        out = np.zeros(3, np.int64)
+        check(self.lib.eals_eval_stats(self.h, _ptr(out)))
+        return {"engine": "tcgen05" if out[0] == 1 else "fp64", "candidates": int(out[1]), "pairs_rescored": int(out[2])}
+
     # ---- instrumentation -----------------------------------------------------------------------------------
     def timings(self):
         ms = np.zeros(6)

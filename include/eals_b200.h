@@ -195,6 +195,11 @@ int eals_evaluate(eals_model* m, const int32_t* gt_items, int32_t topk, int32_t 
                   double sums[3], double* hr, double* ndcg, double* prec, int32_t* count_larger);
 int eals_evaluate_user(eals_model* m, int32_t u, int32_t gt_item, int32_t topk, int32_t mode,
                        double out[3]);
+/* How the last eals_evaluate ran: out[0] = 1 when the scores went through the tcgen05 fp16 filter (lists of
+ * >= 128 users; every close call re-scored in fp64 with the reference's operation order, so the results are
+ * identical to the all-fp64 scan), 0 for the exact fp64 tile scan; out[1] = users whose certain count stayed
+ * <= topK after the filter (candidates), out[2] = (user, item) pairs re-scored exactly. */
+int eals_eval_stats(eals_model* m, int64_t out[3]);
 
 /* Plumbing for the host layer. */
 int eals_leading_dim(const eals_model* m);                 /* ld of U/V/SU/SV rows, in doubles   */

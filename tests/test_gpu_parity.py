@@ -489,3 +489,67 @@ def test_update_model_overwrites_an_existing_rating_with_one():
         port.update_item(i, i + 1)
     assert np.abs(fals.U - port.U).max() < 1e-10 and np.abs(fals.V - port.V).max() < 1e-10
     assert fals.trainMatrix.row_val[row_ptr[u]] == 1.0
+
+
+@pytest.mark.parametrize("K", [8, 64, 128, 130, 200])
+def test_tensor_core_filter_equals_exact_scan(K, monkeypatch):
+    """K3 on tcgen05 (csrc/eval_tc.cuh): fp16 tensor-core scores with a rigorous error bound decide the
+    clear cases, every close call is re-scored in fp64 — count_larger / HR / NDCG / reciprocal rank per user
+    must be IDENTICAL to the all-fp64 tile scan (EALS_EVAL_SCALAR=1) and to the oracle.  Includes exact ties
+    (duplicated item rows score exactly like the held-out item: strict '>' must not count them), a catalogue
+    that is not a multiple of the 128-item tile, several item blocks, and inflated factors (non-zero
+    int-truncated keys for the ranking replay)."""
+    M, N, topK = 1000, 777, 10
+    row_ptr, col_idx = random_csr(M, N, 14, seed=K)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    for _ in range(2):
+        fals.update_user(); port.update_user()
+        fals.update_item(); port.update_item()
+    rng = np.random.default_rng(K + 1)
+    gt = rng.integers(0, N, size=M).astype(np.int32)
+    for variant in ("trained", "ties", "inflated"):
+        U, V = port.U.copy(), port.V.copy()
+        if variant == "ties":
+            for u in range(0, M, 3):                # items scoring EXACTLY like the held-out one
+                V[(gt[u] + 1 + np.arange(5) * 7) % N] = V[gt[u]]
+        if variant == "inflated":
+            U = U * 30 + rng.normal(0, 0.4, U.shape)
+            V = V * 30 + rng.normal(0, 0.4, V.shape)
+        port.U[:], port.V[:] = U, V
+        fals.setUV(U, V)
+        for first_chunk in ("128", None):
+            if first_chunk:
+                monkeypatch.setenv("EALS_EVAL_FIRST_CHUNK", first_chunk)
+            else:
+                monkeypatch.delenv("EALS_EVAL_FIRST_CHUNK", raising=False)
+            for compat in (True, False):
+                want = port.evaluate(gt, topK, compat=compat)
+                monkeypatch.delenv("EALS_EVAL_SCALAR", raising=False)
+                got = fals.evaluate(gt, topK, exact=not compat, per_user=True)
+                assert fals.eval_stats()["engine"] == "tcgen05"
+                monkeypatch.setenv("EALS_EVAL_SCALAR", "1")
+                ref = fals.evaluate(gt, topK, exact=not compat, per_user=True)
+                assert fals.eval_stats()["engine"] == "fp64"
+                monkeypatch.delenv("EALS_EVAL_SCALAR", raising=False)
+                for k in range(1, 5):
+                    assert np.array_equal(got[k], ref[k]), (variant, compat, k)
+                assert np.array_equal(got[4], want[4]) and np.array_equal(got[1], want[1])
+                assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
+
+
+def test_tensor_core_filter_pair_overflow_falls_back_to_exact(monkeypatch):
+    """All-equal scores (zero factors): every item is a candidate for every user; with a tiny pair buffer the
+    filter reports overflow and the exact engine takes over — same answer."""
+    M, N, K = 300, 200, 16
+    row_ptr, col_idx = random_csr(M, N, 8, seed=3)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    Z = np.zeros_like(port.U)
+    port.U[:] = Z
+    fals.setUV(Z, port.V)
+    gt = np.arange(M, dtype=np.int32) % N
+    monkeypatch.setenv("EALS_EVAL_PAIR_CAP", "1000")
+    monkeypatch.setenv("EALS_EVAL_PAIR_HARD_CAP", "5000")
+    got = fals.evaluate(gt, 10, per_user=True)
+    want = port.evaluate(gt, 10, compat=True)
+    assert fals.eval_stats()["engine"] == "fp64"
+    assert np.array_equal(got[4], want[4]) and np.array_equal(got[1], want[1])
