@@ -89,6 +89,36 @@ SIGNATURES = {
     "eals_timings": (C.c_int, [_P, _P]),
     "eals_timings_total": (C.c_int, [_P, _P, _P, C.c_int32]),
     "eals_timings_detail": (C.c_int, [_P, _P, _P]),
+    # eals_group: N ranks in one process (multi-GPU behind the C ABI; virtual ranks on one GPU)
+    "eals_group_create": (C.c_int, [C.POINTER(EalsParams), C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "eals_group_destroy": (C.c_int, [_P]),
+    "eals_group_size": (C.c_int, [_P]),
+    "eals_group_model": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    "eals_group_bounds": (C.c_int, [_P, _P, _P]),
+    "eals_group_set_train": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "eals_group_init_factors": (C.c_int, [_P]),
+    "eals_group_set_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "eals_group_get_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "eals_group_get_factor_row": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "eals_group_get_S": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "eals_group_set_item_weights": (C.c_int, [_P, C.c_int32, _P]),
+    "eals_group_get_item_weights": (C.c_int, [_P, C.c_int32, _P]),
+    "eals_group_update_user": (C.c_int, [_P]),
+    "eals_group_update_item": (C.c_int, [_P]),
+    "eals_group_update_user_row": (C.c_int, [_P, C.c_int32]),
+    "eals_group_update_item_row": (C.c_int, [_P, C.c_int32]),
+    "eals_group_patch_SU": (C.c_int, [_P, _P, _P]),
+    "eals_group_patch_SV": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "eals_group_loss": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "eals_group_predict": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
+    "eals_group_evaluate": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "eals_group_evaluate_user": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "eals_group_sync": (C.c_int, [_P]),
+    "eals_group_replicas_consistent": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "eals_group_save_factors": (C.c_int, [_P, C.c_char_p]),
+    "eals_group_load_factors": (C.c_int, [_P, C.c_char_p]),
+    "eals_group_kernel_launches": (C.c_int64, [_P]),
+    "eals_partition": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
 }
 
 _lib = None

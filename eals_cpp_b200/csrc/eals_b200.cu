@@ -16,6 +16,7 @@
 #include <cstring>
 #include <new>
 #include <random>
+#include <string>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -223,6 +224,7 @@ struct eals_model {
   size_t cap_full_rp = 0, cap_full_cp = 0, cap_full_ci = 0, cap_full_ri = 0, cap_route_tmp = 0;
   eals::PcOut out_to_items = {}, out_to_users = {};   // where the other side's caches live (all ranks)
   int n_ranks = 1, rank = 0;
+  bool local_peers = false;      // peers are plain pointers of models in this process (eals_group), not CUDA IPC mappings
   bool pc_attached = false;      // caches usable: single rank, or both peers' cache sets mapped
   bool pc_users_attached = false, pc_items_attached = false;
   bool pcache_on = false;        // structures built for the current matrix
@@ -363,7 +365,10 @@ int build_routes(eals_model* m, const uint32_t* map, int64_t n, double** stage, 
 // Unmap the other ranks' prediction caches (multi-rank models).
 void close_pc_peers(eals_model* m, eals::PcOut& out, bool& attached_flag) {
   for (int r = 0; r < out.n; r++)
-    if (r != m->rank && out.base[r]) { cudaIpcCloseMemHandle(out.base[r]); out.base[r] = nullptr; }
+    if (r != m->rank && out.base[r]) {
+      if (!m->local_peers) cudaIpcCloseMemHandle(out.base[r]);
+      out.base[r] = nullptr;
+    }
   attached_flag = false;
 }
 
@@ -1102,8 +1107,9 @@ int launch_loss_rows(eals_model* m, const eals::LossSide& a, Side& s, int* n_par
   return EALS_OK;
 }
 
-int loss_terms(eals_model* m, double terms[4]) {
+int loss_terms_enqueue(eals_model* m) {
   if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised");
+  CU(cudaSetDevice(m->p.device));
   tic(m, T_LOSS);
   eals::LossSide a;
   Side& s = m->users;
@@ -1142,9 +1148,19 @@ int loss_terms(eals_model* m, double terms[4]) {
   eals::frob_inner_kernel<<<1, 256, 0, m->stream>>>(su_now, m->SV, m->K, m->LD, m->terms + 3);
   OK(check_launch(m));
   toc(m, T_LOSS);
+  return EALS_OK;
+}
+
+int loss_terms_fetch(eals_model* m, double terms[4]) {
+  CU(cudaSetDevice(m->p.device));
   CU(cudaMemcpyAsync(terms, m->terms, 4 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
   return EALS_OK;
+}
+
+int loss_terms(eals_model* m, double terms[4]) {
+  OK(loss_terms_enqueue(m));
+  return loss_terms_fetch(m, terms);
 }
 
 // ---- evaluation --------------------------------------------------------------------------------
@@ -1211,6 +1227,8 @@ struct eals_eval_ws {
   WsBuf<unsigned long long> counters;   // [0] max |V| bits, [1] pairs, [2] triples
   WsBuf<eals::tc::EvalPair> pairs;
   WsBuf<eals::EvalTriple> triples;
+  WsBuf<unsigned long long> tkey, tkey_out;
+  WsBuf<int32_t> tval, tval_out;
   WsBuf<int32_t> active;
   void release() {
     users.release(); gt.release(); cnt.release(); cnt_exact.release(); list_a.release(); list_b.release(); perm.release();
@@ -1218,6 +1236,7 @@ struct eals_eval_ws {
     un_hat.release(); un_del.release(); un_h.release(); vn_hat.release(); vn_del.release(); vn_h.release();
     sp0.release(); sp1.release(); tile_norm.release(); keys.release(); keys_out.release(); flags.release();
     cub_tmp.release(); counters.release(); pairs.release(); triples.release(); active.release();
+    tkey.release(); tkey_out.release(); tval.release(); tval_out.release();
   }
 };
 
@@ -1231,8 +1250,10 @@ eals_eval_ws& eval_ws(eals_model* m) {
 // ---- scan engine 1: exact fp64 tiles (eval.cuh), item chunks with an early-out of decided users --------
 // Used for short user lists (evaluate_for_user), as the engine the tensor filter is tested against
 // (EALS_EVAL_SCALAR=1) and as its fall-back when the candidate list overflows.
+// Both engines hand the ranking replay the (slot, item, (int)score) triples of the surviving users as two
+// parallel arrays sorted by (slot, item): tkey = slot << 32 | item, tval = (int)score.
 int scan_exact(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples,
-               std::vector<int32_t>& cnt, std::vector<eals::EvalTriple>& tr) {
+               std::vector<int32_t>& cnt, std::vector<unsigned long long>& tkey, std::vector<int32_t>& tval) {
   eals_eval_ws& ws = eval_ws(m);
   const int K = m->K, LD = m->LD, N = m->N;
   OK(ws.cnt.reserve((size_t)n));
@@ -1310,8 +1331,16 @@ int scan_exact(eals_model* m, int n, const int32_t* d_users, const double* d_gts
     if (got <= cap) break;
     cap = got;  // exact size known now: the second pass cannot overflow
   }
-  tr.resize((size_t)got);
+  std::vector<eals::EvalTriple> tr((size_t)got);
   if (got) CU(cudaMemcpy(tr.data(), ws.triples.p, sizeof(eals::EvalTriple) * got, cudaMemcpyDeviceToHost));
+  std::sort(tr.begin(), tr.end(), [](const eals::EvalTriple& a, const eals::EvalTriple& b) {
+    return a.slot != b.slot ? a.slot < b.slot : a.item < b.item;
+  });
+  tkey.resize(tr.size()); tval.resize(tr.size());
+  for (size_t t = 0; t < tr.size(); t++) {
+    tkey[t] = ((unsigned long long)(uint32_t)tr[t].slot << 32) | (uint32_t)tr[t].item;
+    tval[t] = tr[t].key;
+  }
   return EALS_OK;
 }
 
@@ -1359,11 +1388,22 @@ int launch_filter_k(eals_model* m, int nkc, const CUtensorMap& mapU, const CUten
 // survivors' triples out of the re-scored candidate pairs
 __global__ void pairs_to_triples_kernel(const eals::tc::EvalPair* __restrict__ pairs, const unsigned long long* __restrict__ n_pairs,
                                         const int32_t* __restrict__ cnt_hi, const int32_t* __restrict__ cnt_exact, int topk,
-                                        eals::EvalTriple* __restrict__ out, unsigned long long* __restrict__ n_out) {
+                                        unsigned long long* __restrict__ out_key, int32_t* __restrict__ out_val,
+                                        unsigned long long* __restrict__ n_out) {
   const unsigned long long n = *n_pairs;
   for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
     const eals::tc::EvalPair pr = pairs[t];
-    if (pr.key != 0 && cnt_hi[pr.slot] <= topk && cnt_exact[pr.slot] <= topk) out[atomicAdd(n_out, 1ull)] = eals::EvalTriple{pr.slot, pr.item, pr.key};
+    const bool keep = pr.key != 0 && cnt_hi[pr.slot] <= topk && cnt_exact[pr.slot] <= topk;
+    // warp-aggregated append (tens of millions of keys at the 10M x 2M scale)
+    const unsigned ballot = __ballot_sync(__activemask(), keep);
+    if (!keep) continue;
+    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(ballot, base, leader);
+    const unsigned long long pos = base + __popc(ballot & ((1u << lane) - 1u));
+    out_key[pos] = ((unsigned long long)(uint32_t)pr.slot << 32) | (uint32_t)pr.item;
+    out_val[pos] = pr.key;
   }
 }
 
@@ -1372,10 +1412,11 @@ __global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
 struct TcStats { long long candidates = 0, pairs = 0, blocks = 0; };
 
 int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples,
-            std::vector<int32_t>& cnt, std::vector<eals::EvalTriple>& tr, bool* overflow) {
+            std::vector<int32_t>& cnt, std::vector<unsigned long long>& tkey, std::vector<int32_t>& tval, bool* overflow) {
   namespace tc = eals::tc;
   eals_eval_ws& ws = eval_ws(m);
   *overflow = false;
+  StageTimer tm;
   const int K = m->K, LD = m->LD, N = m->N;
   const int nkc = (K + tc::kKC - 1) / tc::kKC, KP = nkc * tc::kKC;
   const int n_tiles = (N + tc::kTN - 1) / tc::kTN;
@@ -1434,6 +1475,7 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
   int32_t* d_n = ws.scalars.p;          // [0]: size of the current working list, [1]: next
   set_i32_kernel<<<1, 1, 0, st>>>(d_n, n);
   OK(check_launch(m));
+  tm.lap("eval: fp16 copies, norms, item order");
 
   // ---- MODE 0 over L2-sized item blocks, working set compacted on the device between them ----
   tc::TcArgs a{};
@@ -1464,6 +1506,13 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
     a.it0 = (int)(i0 / tc::kTN); a.it1 = (int)((i1 + tc::kTN - 1) / tc::kTN);
     OK(launch_filter_k<0>(m, nkc, list ? mapW : mapU0, mapV, a, max_works));
     OK(compact());
+    if (tm.on) {
+      int left = 0;
+      cudaMemcpy(&left, d_n, sizeof(int), cudaMemcpyDeviceToHost);
+      char what[96];
+      snprintf(what, sizeof(what), "eval: items [%lld, %lld) -> %d undecided", (long long)i0, (long long)i1, left);
+      tm.lap(what);
+    }
     i0 = (int64_t)a.it1 * tc::kTN;
     blk = std::min<int64_t>(blk * 4, 262144);
   }
@@ -1490,26 +1539,43 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
       if (attempt == 1 || got > hard_cap) { *overflow = true; return EALS_OK; }   // degenerate scores: exact engine instead
       cap = got;
     }
+    tm.lap("eval: candidate emission (MODE 1)");
     if (got) {
       tc::eval_rescore_kernel<<<8 * m->sm_count, 256, 0, st>>>(m->U, m->V, K, LD, d_users, 0, d_gts, ws.pairs.p, d_np, got, ws.cnt_exact.p);
       OK(check_launch(m));
     }
   }
+  tm.lap("eval: exact re-score");
   std::vector<int32_t> hi((size_t)n), ex((size_t)n);
   CU(cudaMemcpyAsync(hi.data(), ws.cnt.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(ex.data(), ws.cnt_exact.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   unsigned long long n_tr = 0;
   if (want_triples && got) {
-    OK(ws.triples.reserve((size_t)got));
+    OK(ws.tkey.reserve((size_t)got)); OK(ws.tval.reserve((size_t)got));
     unsigned long long* d_nt = ws.counters.p + 2;
-    pairs_to_triples_kernel<<<8 * m->sm_count, 256, 0, st>>>(ws.pairs.p, d_np, ws.cnt.p, ws.cnt_exact.p, topk, ws.triples.p, d_nt);
+    pairs_to_triples_kernel<<<8 * m->sm_count, 256, 0, st>>>(ws.pairs.p, d_np, ws.cnt.p, ws.cnt_exact.p, topk, ws.tkey.p, ws.tval.p, d_nt);
     OK(check_launch(m));
     CU(cudaMemcpyAsync(&n_tr, d_nt, sizeof(n_tr), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
   for (int s = 0; s < n; s++) cnt[s] = hi[s] > topk ? topk + 1 : ex[s];
-  tr.resize((size_t)n_tr);
-  if (n_tr) CU(cudaMemcpy(tr.data(), ws.triples.p, sizeof(eals::EvalTriple) * n_tr, cudaMemcpyDeviceToHost));
+  tkey.resize((size_t)n_tr); tval.resize((size_t)n_tr);
+  if (n_tr) {   // (slot, item) order on the device, then one copy each
+    if (n_tr >= 0x7fffffffull) return fail(EALS_ERR_UNSUPPORTED, "too many ranking keys (%llu)", n_tr);
+    OK(ws.tkey_out.reserve((size_t)n_tr)); OK(ws.tval_out.reserve((size_t)n_tr));
+    size_t tmp = 0;
+    int slot_bits = 1;
+    while ((1ll << slot_bits) < n) slot_bits++;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, ws.tkey.p, ws.tkey_out.p, ws.tval.p, ws.tval_out.p, (int)n_tr, 0, 32 + slot_bits, st);
+    OK(ws.cub_tmp.reserve(tmp + 16));
+    if (cub::DeviceRadixSort::SortPairs(ws.cub_tmp.p, tmp, ws.tkey.p, ws.tkey_out.p, ws.tval.p, ws.tval_out.p, (int)n_tr, 0, 32 + slot_bits, st) != cudaSuccess)
+      return fail(EALS_ERR_CUDA, "ranking key sort");
+    m->launches++;
+    CU(cudaMemcpyAsync(tkey.data(), ws.tkey_out.p, sizeof(unsigned long long) * n_tr, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tval.data(), ws.tval_out.p, sizeof(int32_t) * n_tr, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  tm.lap("eval: counts + keys to host");
   if (getenv("EALS_VERBOSE") && getenv("EALS_VERBOSE")[0] == '1')
     fprintf(stderr, "[eals] evaluate (tcgen05 filter): %d users, %d candidates after the certain count, %llu pairs re-scored exactly, %llu keys\n",
             n, n_cand, got, n_tr);
@@ -1532,38 +1598,44 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
   eals::eval_gt_score_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->U, m->V, ws.gt.p, ws.users.p, 0, n, K, LD, ws.gts.p);
   OK(check_launch(m));
   std::vector<int32_t> cnt((size_t)n, 0);
-  std::vector<eals::EvalTriple> tr;
+  std::vector<unsigned long long> tkey;
+  std::vector<int32_t> tval;
   const bool want_triples = mode != EALS_EVAL_EXACT;
   const bool scalar_only = getenv("EALS_EVAL_SCALAR") && getenv("EALS_EVAL_SCALAR")[0] == '1';
   bool done = false;
   m->eval_engine = 0;
   if (n >= kTcMinUsers && K <= 256 && !scalar_only) {
     bool overflow = false;
-    OK(scan_tc(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tr, &overflow));
+    OK(scan_tc(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tkey, tval, &overflow));
     done = !overflow;
     if (done) m->eval_engine = 1;
   }
-  if (!done) OK(scan_exact(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tr));
+  if (!done) OK(scan_exact(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tkey, tval));
+  StageTimer tm_host;
 
   std::vector<int> pos((size_t)n, -1);
   if (mode == EALS_EVAL_EXACT) {
     for (int s = 0; s < n; s++)
       if (cnt[s] < topk) pos[s] = cnt[s];
   } else {
-    // replay of the reference's ranking for the survivors of the early-out (countLarger > topK -> zeros,
-    // MF_fastALS.cpp:633-634); triples carry the slot, the (item, key) stream of a slot ascends by item
-    std::sort(tr.begin(), tr.end(), [](const eals::EvalTriple& a, const eals::EvalTriple& b) {
-      return a.slot != b.slot ? a.slot < b.slot : a.item < b.item;
+    // Replay of the reference's ranking for the survivors of the early-out (countLarger > topK -> zeros,
+    // MF_fastALS.cpp:633-634) with the real libstdc++ partial_sort_copy, the survivors spread over the host
+    // threads; a survivor's (item, key) stream is its range of the sorted key arrays.
+    std::vector<int32_t> surv;
+    for (int s = 0; s < n; s++)
+      if (cnt[s] <= topk) surv.push_back(s);
+    parallel_chunks((int64_t)surv.size(), nullptr, [&](int, int64_t b0, int64_t b1) {
+      std::vector<std::pair<int, int>> nz;
+      for (int64_t t = b0; t < b1; t++) {
+        const int s = surv[(size_t)t];
+        const unsigned long long lo = (unsigned long long)(uint32_t)s << 32;
+        size_t q = (size_t)(std::lower_bound(tkey.begin(), tkey.end(), lo) - tkey.begin());
+        nz.clear();
+        for (; q < tkey.size() && (tkey[q] >> 32) == (unsigned long long)(uint32_t)s; q++)
+          nz.emplace_back((int)(tkey[q] & 0xffffffffu), tval[q]);
+        pos[(size_t)s] = reference_rank(nz, N, topk, gt_slot_h[s]);
+      }
     });
-    size_t q = 0;
-    std::vector<std::pair<int, int>> nz;
-    for (int s = 0; s < n; s++) {
-      if (cnt[s] > topk) continue;
-      nz.clear();
-      while (q < tr.size() && tr[q].slot < s) q++;
-      while (q < tr.size() && tr[q].slot == s) { nz.emplace_back(tr[q].item, tr[q].key); q++; }
-      pos[s] = reference_rank(nz, N, topk, gt_slot_h[s]);
-    }
   }
   for (int s = 0; s < n; s++) {
     double r0 = 0, r1 = 0, r2 = 0;
@@ -1574,6 +1646,7 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
     if (count_larger) count_larger[s] = std::min(cnt[s], topk + 1);
     sums[0] += r0; sums[1] += r1; sums[2] += r2;
   }
+  tm_host.lap("eval: host ranking replay + metrics");
   return EALS_OK;
 }
 
@@ -2084,7 +2157,8 @@ int eals_ipc_detach(eals_model* m) {
   cudaSetDevice(m->p.device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   for (eals::PeerSet* ps : {&m->peersU, &m->peersV}) {
-    for (int p = 0; p < ps->n; p++) cudaIpcCloseMemHandle(ps->x[p]);
+    if (!m->local_peers)
+      for (int p = 0; p < ps->n; p++) cudaIpcCloseMemHandle(ps->x[p]);
     ps->n = 0;
   }
   if (m->n_ranks > 1) {
@@ -2199,3 +2273,5 @@ int eals_timings_detail(eals_model* m, double ms[6], int64_t calls[6]) {
 }
 
 }  // extern "C"
+
+#include "group.cuh"

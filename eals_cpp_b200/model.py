@@ -693,3 +693,207 @@ class MF_fastALS:
 
     def owned_nnz(self) -> int:
         return int(self.lib.eals_nnz(self.h))
+
+
+# --------------------------------------------------------------------------------------------------
+# The same class over eals_group: N ranks in ONE process (include/eals_b200.h, "eals_group").
+# --------------------------------------------------------------------------------------------------
+class GroupMF_fastALS:
+    """``MF_fastALS`` with the multi-GPU split behind the C ABI: one process, one host thread, rank r on
+    ``devices[r]``.  ``devices=[0, 0, 0, 0]`` runs four *virtual ranks* on one GPU — the whole sharded path
+    (cost-model partition, peer stores of finished rows, routed prediction caches, fixed-order all-reduce of
+    the partial Grams, setTrain re-attachment) without needing four GPUs; this is what the 1-GPU CI runs.
+    Same method names and meanings as ``MF_fastALS`` (MF_fastALS.h:52-72)."""
+
+    def __init__(self, trainMatrix: SparseMat, testRatings, topK=10, threadNum=1, factors=64, maxIter=20,
+                 w0=10.0, alpha=0.75, reg=0.01, init_mean=0.0, init_stdev=0.01, showProgress=False,
+                 showLoss=True, userCount=None, itemCount=None, *, devices=(0,), init=True, out=None):
+        self.lib = _lib.load()
+        sm = self.trainMatrix = trainMatrix
+        self.userCount, self.itemCount = int(userCount or sm.M), int(itemCount or sm.N)
+        self.topK, self.factors, self.maxIter = int(topK), int(factors), int(maxIter)
+        self.w0, self.alpha, self.reg = float(w0), float(alpha), float(reg)
+        self.showloss = bool(showLoss)
+        del threadNum, showProgress
+        self.out = out or sys.stdout
+        self.devices = [int(d) for d in devices]
+        self.world = len(self.devices)
+        self.testItems = None if testRatings is None else np.ascontiguousarray(testRatings, np.int32)
+        p = EalsParams()
+        self.lib.eals_default_params(C.byref(p))
+        p.n_users, p.n_items, p.factors, p.topk = sm.M, sm.N, self.factors, self.topK
+        p.w0, p.alpha, p.reg = self.w0, self.alpha, self.reg
+        p.init_mean, p.init_stdev = float(init_mean), float(init_stdev)
+        p.input_space = _lib.EALS_DEVICE if sm.on_device else _lib.EALS_HOST
+        dev = np.ascontiguousarray(self.devices, np.int32)
+        g = C.c_void_p()
+        check(self.lib.eals_group_create(C.byref(p), self.world, _ptr(dev), _ptr(sm.row_ptr), _ptr(sm.col_idx),
+                                         _ptr(sm.row_val), _ptr(sm.col_ptr), _ptr(sm.row_idx), _ptr(sm.col_val), C.byref(g)))
+        self.g = g
+        ub, ib = np.zeros(self.world + 1, np.int32), np.zeros(self.world + 1, np.int32)
+        check(self.lib.eals_group_bounds(self.g, _ptr(ub), _ptr(ib)))
+        self.user_bounds, self.item_bounds = ub.tolist(), ib.tolist()
+        if init:
+            check(self.lib.eals_group_init_factors(self.g))
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.lib.eals_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rank_model(self, r):
+        h = C.c_void_p()
+        check(self.lib.eals_group_model(self.g, int(r), C.byref(h)))
+        return h
+
+    def rank_factors(self, r):
+        """(U, V) replicas of rank r as host arrays."""
+        U, V = np.empty((self.userCount, self.factors)), np.empty((self.itemCount, self.factors))
+        check(self.lib.eals_get_factors(self.rank_model(r), _lib.EALS_HOST, _ptr(U), _ptr(V)))
+        return U, V
+
+    def rank_S(self, r):
+        SU, SV = np.empty((self.factors, self.factors)), np.empty((self.factors, self.factors))
+        check(self.lib.eals_get_S(self.rank_model(r), _lib.EALS_HOST, _ptr(SU), _ptr(SV)))
+        return SU, SV
+
+    U = property(lambda s: s.rank_factors(0)[0])
+    V = property(lambda s: s.rank_factors(0)[1])
+    SU = property(lambda s: s.rank_S(0)[0])
+    SV = property(lambda s: s.rank_S(0)[1])
+
+    @property
+    def Wi(self):
+        w = np.empty(self.itemCount)
+        check(self.lib.eals_group_get_item_weights(self.g, _lib.EALS_HOST, _ptr(w)))
+        return w
+
+    @Wi.setter
+    def Wi(self, w):
+        w = np.ascontiguousarray(w, np.float64)
+        check(self.lib.eals_group_set_item_weights(self.g, _lib.EALS_HOST, _ptr(w)))
+
+    def sync(self):
+        check(self.lib.eals_group_sync(self.g))
+
+    def setUV(self, U, V):
+        U = None if U is None else np.ascontiguousarray(U, np.float64)
+        V = None if V is None else np.ascontiguousarray(V, np.float64)
+        check(self.lib.eals_group_set_factors(self.g, _lib.EALS_HOST, _ptr(U), _ptr(V)))
+
+    def setTrain(self, sm: SparseMat):
+        space = _lib.EALS_DEVICE if sm.on_device else _lib.EALS_HOST
+        check(self.lib.eals_group_set_train(self.g, space, _ptr(sm.row_ptr), _ptr(sm.col_idx), _ptr(sm.row_val),
+                                            _ptr(sm.col_ptr), _ptr(sm.row_idx), _ptr(sm.col_val)))
+        self.trainMatrix = sm
+
+    def update_user(self):
+        check(self.lib.eals_group_update_user(self.g))
+
+    def update_item(self):
+        check(self.lib.eals_group_update_item(self.g))
+
+    def runOneIteration(self):
+        self.update_user()
+        self.update_item()
+
+    def update_user_thread(self, u):
+        check(self.lib.eals_group_update_user_row(self.g, int(u)))
+
+    def update_item_thread(self, i):
+        check(self.lib.eals_group_update_item_row(self.g, int(i)))
+
+    def update_user_SU(self, oldVector, uget):
+        o, n = np.ascontiguousarray(oldVector, np.float64), np.ascontiguousarray(uget, np.float64)
+        check(self.lib.eals_group_patch_SU(self.g, _ptr(o), _ptr(n)))
+
+    def update_item_SV(self, i, oldVector, vget):
+        o, n = np.ascontiguousarray(oldVector, np.float64), np.ascontiguousarray(vget, np.float64)
+        check(self.lib.eals_group_patch_SV(self.g, int(i), _ptr(o), _ptr(n)))
+
+    def _factor_row(self, which, r):
+        out = np.empty(self.factors)
+        check(self.lib.eals_group_get_factor_row(self.g, which, int(r), _ptr(out)))
+        return out
+
+    def updateModel(self, u, i, patch_S=True, maxIterOnline=10):
+        """Online update on a sharded model (MF_fastALS.cpp:223-242): the owner of user u / item i runs the
+        single-row kernel, which stores the new row into every replica; the S patches go to every rank."""
+        u, i = int(u), int(i)
+        grown = insert_interaction(self.trainMatrix, u, i)
+        if grown is not None:
+            self.setTrain(grown)
+        Wi = self.Wi
+        if Wi[i] == 0.0:
+            Wi[i] = self.w0 / self.itemCount
+            self.Wi = Wi
+        for _ in range(int(maxIterOnline)):
+            old = self._factor_row(_lib.BUF_U, u) if patch_S else None
+            self.update_user_thread(u)
+            if patch_S:
+                self.update_user_SU(old, self._factor_row(_lib.BUF_U, u))
+            old = self._factor_row(_lib.BUF_V, i) if patch_S else None
+            self.update_item_thread(i)
+            if patch_S:
+                self.update_item_SV(i, old, self._factor_row(_lib.BUF_V, i))
+
+    def loss(self) -> float:
+        v = C.c_double()
+        check(self.lib.eals_group_loss(self.g, C.byref(v)))
+        return v.value
+
+    def predict(self, u, i) -> float:
+        s = C.c_double()
+        check(self.lib.eals_group_predict(self.g, int(u), int(i), C.byref(s)))
+        return s.value
+
+    def evaluate(self, testRatings=None, topK=None, exact=False, per_user=False):
+        items = self.testItems if testRatings is None else np.ascontiguousarray(testRatings, np.int32)
+        topK = int(topK or self.topK)
+        means = np.zeros(3)
+        hr = ndcg = prec = cnt = None
+        if per_user:
+            hr, ndcg, prec = np.zeros(self.userCount), np.zeros(self.userCount), np.zeros(self.userCount)
+            cnt = np.zeros(self.userCount, np.int32)
+        check(self.lib.eals_group_evaluate(self.g, _ptr(items), topK, _lib.EVAL_EXACT if exact else _lib.EVAL_REFERENCE,
+                                           _ptr(means), _ptr(hr), _ptr(ndcg), _ptr(prec), _ptr(cnt)))
+        return (means, hr, ndcg, prec, cnt) if per_user else means
+
+    def replicas_consistent(self) -> bool:
+        ok = C.c_int32()
+        check(self.lib.eals_group_replicas_consistent(self.g, C.byref(ok)))
+        return bool(ok.value)
+
+    def save(self, path):
+        check(self.lib.eals_group_save_factors(self.g, os.fsencode(path)))
+
+    def load(self, path):
+        check(self.lib.eals_group_load_factors(self.g, os.fsencode(path)))
+
+    def buildModel(self):
+        loss_pre = float("inf")
+        self.losses = []
+        for it in range(self.maxIter):
+            t0 = time.perf_counter()
+            self.update_user(); self.sync()
+            t_user = time.perf_counter() - t0
+            print(f"Time of user_update: {t_user:g}", file=self.out)
+            t0 = time.perf_counter()
+            self.update_item(); self.sync()
+            t_item = time.perf_counter() - t0
+            print(f"Time of item_update: {t_item:g}", file=self.out)
+            if self.showloss:
+                t0 = time.perf_counter()
+                cur = self.loss()
+                print(f"Iter={it} {t_user + t_item:g} {'-' if loss_pre >= cur else '+'} loss:{cur:g} {time.perf_counter() - t0:g}", file=self.out)
+                loss_pre = cur
+                self.losses.append(cur)
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.eals_group_kernel_launches(self.g))

@@ -249,6 +249,56 @@ int eals_timings_total(eals_model* m, double ms[6], int64_t calls[6], int32_t re
  * [3..5] the same for the item side.  Query BEFORE eals_timings_total(reset=1). */
 int eals_timings_detail(eals_model* m, double ms[6], int64_t calls[6]);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * eals_group — N GPUs of one box behind ONE object, driven by ONE host thread like the reference's class
+ * (MF_fastALS.h:52-55 ctor, MF_fastALS.cpp:112-161 buildModel).  Rank r lives on devices[r] (NULL: 0..N-1)
+ * and owns a contiguous user range and item range, chosen by a per-row cost model (eals_partition); U and V
+ * are replicated.  A half-epoch is: every rank's sweep (finished rows stored into ALL replicas by the
+ * kernels themselves, over NVLink peer pointers), every rank's partial K x K Gram, and a one-shot
+ * all-reduce over peer memory that adds the partials in rank order (all ranks end with bit-identical
+ * S caches).  Everything is ordered by CUDA events between the ranks' streams; no call below synchronises
+ * the host inside an epoch.  `devices` may repeat a GPU ("virtual ranks": the whole sharded path on one
+ * GPU — how single-GPU CI covers it).  All other entry points mean what their eals_* namesakes mean, over
+ * the whole matrix; evaluation outputs are indexed by GLOBAL user id and `means` are already divided by
+ * n_users. */
+typedef struct eals_group eals_group;
+int eals_group_create(const eals_params* params, int32_t n_ranks, const int32_t* devices,
+                      const int64_t* row_ptr, const int32_t* col_idx, const double* row_val,
+                      const int64_t* col_ptr, const int32_t* row_idx, const double* col_val, eals_group** out);
+int eals_group_destroy(eals_group* g);
+int eals_group_size(const eals_group* g);
+int eals_group_model(eals_group* g, int32_t rank, eals_model** out);        /* borrowed: timings, buffers, hashes */
+int eals_group_bounds(const eals_group* g, int32_t* user_bounds, int32_t* item_bounds);   /* n_ranks + 1 each */
+int eals_group_set_train(eals_group* g, int32_t input_space, const int64_t* row_ptr, const int32_t* col_idx,
+                         const double* row_val, const int64_t* col_ptr, const int32_t* row_idx, const double* col_val);
+int eals_group_init_factors(eals_group* g);
+int eals_group_set_factors(eals_group* g, int32_t space, const double* U, const double* V);
+int eals_group_get_factors(eals_group* g, int32_t space, double* U, double* V);
+int eals_group_get_factor_row(eals_group* g, int32_t which, int32_t row, double* out);
+int eals_group_get_S(eals_group* g, int32_t space, double* SU, double* SV);
+int eals_group_set_item_weights(eals_group* g, int32_t space, const double* Wi);
+int eals_group_get_item_weights(eals_group* g, int32_t space, double* Wi);
+int eals_group_update_user(eals_group* g);                                  /* MF_fastALS.cpp:127-132 */
+int eals_group_update_item(eals_group* g);                                  /* MF_fastALS.cpp:146-152 */
+int eals_group_update_user_row(eals_group* g, int32_t u);                   /* update_user_thread(u)  */
+int eals_group_update_item_row(eals_group* g, int32_t i);                   /* update_item_thread(i)  */
+int eals_group_patch_SU(eals_group* g, const double* old_row, const double* new_row);
+int eals_group_patch_SV(eals_group* g, int32_t i, const double* old_row, const double* new_row);
+int eals_group_loss(eals_group* g, double* loss);
+int eals_group_predict(eals_group* g, int32_t u, int32_t i, double* score);
+int eals_group_evaluate(eals_group* g, const int32_t* gt_items, int32_t topk, int32_t mode, double means[3],
+                        double* hr, double* ndcg, double* prec, int32_t* count_larger);
+int eals_group_evaluate_user(eals_group* g, int32_t u, int32_t gt_item, int32_t topk, int32_t mode, double out[3]);
+int eals_group_sync(eals_group* g);
+int eals_group_replicas_consistent(eals_group* g, int32_t* ok);             /* all U / V replicas bit-identical */
+int eals_group_save_factors(eals_group* g, const char* path);
+int eals_group_load_factors(eals_group* g, const char* path);
+int64_t eals_group_kernel_launches(const eals_group* g);
+/* Row ranges of (nearly) equal COST for n_ranks ranks: bounds[0] = 0 <= ... <= bounds[n_ranks] = n_rows.  The
+ * cost of a row follows the kernel family its length selects (ns per row / per nonzero measured on B200).
+ * `ptr` is the host offsets array of that orientation. */
+int eals_partition(const int64_t* ptr, int32_t n_rows, int32_t n_ranks, int32_t* bounds);
+
 #ifdef __cplusplus
 }
 #endif
