@@ -1185,12 +1185,25 @@ int reference_rank(const std::vector<std::pair<int, int>>& nz, int n_items, int 
     seq.emplace_back(i, key);
   }
   if (any_negative) {
-    // a zero key can displace a negative heap top: keep the whole item list
-    for (int i = head; i < n_items; i++) {
+    // A negative heap top is displaced by ANY later element with a larger key — zero keys included.  Every
+    // accepted element with key >= 0 removes one negative key from the heap for good (it replaces the top,
+    // the most negative one), and while a negative is left every element with key >= 0 is accepted.  So the
+    // first `neg` non-negative elements after the head matter (walking the items in id order, zeros and
+    // listed keys merged), negative keys in that stretch may matter too, and from then on the heap top is
+    // >= 0: only positive keys can pass comp(e, top).  (The full 2M-item list per such user made the replay
+    // 0.4 s at 10M x 2M.)
+    int neg = 0;
+    for (const auto& e : seq) neg += e.second < 0;
+    int i = head;
+    while (neg > 0 && i < n_items) {
       int key = 0;
       if (q < nz.size() && nz[q].first == i) key = nz[q++].second;
       seq.emplace_back(i, key);
+      if (key >= 0) neg--;
+      i++;
     }
+    for (; q < nz.size(); q++)
+      if (nz[q].second > 0) seq.push_back(nz[q]);
   } else {
     // heap top stays >= 0: only positive keys can ever pass comp(e, top)
     for (; q < nz.size(); q++)
@@ -1214,7 +1227,24 @@ struct WsBuf {
 
 }  // namespace
 
+// Pinned host staging (grow-only): the ranking keys of a 10M-user evaluation are ~300 MB, pageable copies of
+// that size run at a few GB/s.
+struct PinnedBuf {
+  unsigned char* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return EALS_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    CU(cudaHostAlloc((void**)&p, bytes + bytes / 8 + 64, cudaHostAllocDefault));
+    cap = bytes + bytes / 8 + 64;
+    return EALS_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct eals_eval_ws {
+  PinnedBuf host;
   WsBuf<int32_t> users, gt, cnt, cnt_exact, list_a, list_b, perm, ids, exps, scalars;
   WsBuf<double> gts;
   WsBuf<__half> Uh, Vh, W;
@@ -1236,7 +1266,7 @@ struct eals_eval_ws {
     un_hat.release(); un_del.release(); un_h.release(); vn_hat.release(); vn_del.release(); vn_h.release();
     sp0.release(); sp1.release(); tile_norm.release(); keys.release(); keys_out.release(); flags.release();
     cub_tmp.release(); counters.release(); pairs.release(); triples.release(); active.release();
-    tkey.release(); tkey_out.release(); tval.release(); tval_out.release();
+    tkey.release(); tkey_out.release(); tval.release(); tval_out.release(); host.release();
   }
 };
 
@@ -1250,11 +1280,22 @@ eals_eval_ws& eval_ws(eals_model* m) {
 // ---- scan engine 1: exact fp64 tiles (eval.cuh), item chunks with an early-out of decided users --------
 // Used for short user lists (evaluate_for_user), as the engine the tensor filter is tested against
 // (EALS_EVAL_SCALAR=1) and as its fall-back when the candidate list overflows.
-// Both engines hand the ranking replay the (slot, item, (int)score) triples of the surviving users as two
-// parallel arrays sorted by (slot, item): tkey = slot << 32 | item, tval = (int)score.
-int scan_exact(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples,
-               std::vector<int32_t>& cnt, std::vector<unsigned long long>& tkey, std::vector<int32_t>& tval) {
+// What both scan engines hand back: the users that survive the reference's early-out (count_larger <= topK,
+// MF_fastALS.cpp:633-634) with their exact counts — every other user is decided (zeros) — and, for the
+// ranking replay, the survivors' (slot, item, (int)score) triples with a non-zero key as two parallel arrays
+// sorted by (slot, item): key = slot << 32 | item, val = (int)score.
+struct ScanResult {
+  std::vector<int32_t> surv_slot, surv_cnt;      // ascending slot
+  std::vector<unsigned long long> own_key;       // storage when the arrays do not live in the pinned staging
+  std::vector<int32_t> own_val;
+  const unsigned long long* key = nullptr;
+  const int32_t* val = nullptr;
+  size_t n_keys = 0;
+};
+
+int scan_exact(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples, ScanResult& out) {
   eals_eval_ws& ws = eval_ws(m);
+  std::vector<int32_t> cnt((size_t)n, 0);
   const int K = m->K, LD = m->LD, N = m->N;
   OK(ws.cnt.reserve((size_t)n));
   OK(ws.active.reserve((size_t)n));
@@ -1303,13 +1344,15 @@ int scan_exact(eals_model* m, int n, const int32_t* d_users, const double* d_gts
       active.resize(keep);
     }
   }
-  if (!want_triples) return EALS_OK;
-  // survivors of the early-out: the (item, (int)score) pairs with a non-zero key
-  std::vector<int32_t> surv;
+  // survivors of the early-out
+  std::vector<int32_t>& surv = out.surv_slot;
+  surv.clear(); out.surv_cnt.clear();
   for (int s = 0; s < n; s++)
-    if (cnt[s] <= topk) surv.push_back(s);
+    if (cnt[s] <= topk) { surv.push_back(s); out.surv_cnt.push_back(cnt[s]); }
+  out.key = nullptr; out.val = nullptr; out.n_keys = 0;
   const int ns = (int)surv.size();
-  if (ns == 0) return EALS_OK;
+  if (!want_triples || ns == 0) return EALS_OK;
+  // ... and their (item, (int)score) pairs with a non-zero key
   CU(cudaMemcpyAsync(d_active, surv.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, m->stream));
   OK(ws.counters.reserve(4));
   unsigned long long* d_nt = ws.counters.p + 2;
@@ -1336,11 +1379,12 @@ int scan_exact(eals_model* m, int n, const int32_t* d_users, const double* d_gts
   std::sort(tr.begin(), tr.end(), [](const eals::EvalTriple& a, const eals::EvalTriple& b) {
     return a.slot != b.slot ? a.slot < b.slot : a.item < b.item;
   });
-  tkey.resize(tr.size()); tval.resize(tr.size());
+  out.own_key.resize(tr.size()); out.own_val.resize(tr.size());
   for (size_t t = 0; t < tr.size(); t++) {
-    tkey[t] = ((unsigned long long)(uint32_t)tr[t].slot << 32) | (uint32_t)tr[t].item;
-    tval[t] = tr[t].key;
+    out.own_key[t] = ((unsigned long long)(uint32_t)tr[t].slot << 32) | (uint32_t)tr[t].item;
+    out.own_val[t] = tr[t].key;
   }
+  out.key = out.own_key.data(); out.val = out.own_val.data(); out.n_keys = tr.size();
   return EALS_OK;
 }
 
@@ -1369,9 +1413,10 @@ template <int NKC, int MODE>
 int launch_filter(eals_model* m, const CUtensorMap& mapU, const CUtensorMap& mapV, const eals::tc::TcArgs& a, int max_works) {
   using C = eals::tc::Cfg<NKC>;
   auto kern = eals::tc::eval_filter_kernel<NKC, MODE>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-  const int grid = std::max(1, std::min(m->sm_count, max_works));
-  kern<<<grid, eals::tc::kThreads, C::kSmem, m->stream>>>(mapU, mapV, a);
+  const size_t smem = MODE == 1 ? C::kSmemEmit : C::kSmem;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  (void)max_works;     // the kernel cuts the item range into chunks when there are fewer user tiles than SMs
+  kern<<<m->sm_count, eals::tc::kThreads, smem, m->stream>>>(mapU, mapV, a);
   return check_launch(m);
 }
 template <int MODE>
@@ -1411,8 +1456,7 @@ __global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
 
 struct TcStats { long long candidates = 0, pairs = 0, blocks = 0; };
 
-int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples,
-            std::vector<int32_t>& cnt, std::vector<unsigned long long>& tkey, std::vector<int32_t>& tval, bool* overflow) {
+int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, int topk, bool want_triples, ScanResult& out, bool* overflow) {
   namespace tc = eals::tc;
   eals_eval_ws& ws = eval_ws(m);
   *overflow = false;
@@ -1546,10 +1590,16 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
     }
   }
   tm.lap("eval: exact re-score");
-  std::vector<int32_t> hi((size_t)n), ex((size_t)n);
-  CU(cudaMemcpyAsync(hi.data(), ws.cnt.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(ex.data(), ws.cnt_exact.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  // candidates and their exact counts (a few per cent of the users at most); everybody else is decided
+  std::vector<int32_t> cand((size_t)n_cand), cand_cnt((size_t)n_cand);
   unsigned long long n_tr = 0;
+  if (n_cand > 0) {
+    OK(ws.active.reserve((size_t)n_cand));
+    eals::gather_i32_kernel<<<(n_cand + 255) / 256, 256, 0, st>>>(ws.cnt_exact.p, list, n_cand, ws.active.p);
+    OK(check_launch(m));
+    CU(cudaMemcpyAsync(cand.data(), list, sizeof(int32_t) * n_cand, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cand_cnt.data(), ws.active.p, sizeof(int32_t) * n_cand, cudaMemcpyDeviceToHost, st));
+  }
   if (want_triples && got) {
     OK(ws.tkey.reserve((size_t)got)); OK(ws.tval.reserve((size_t)got));
     unsigned long long* d_nt = ws.counters.p + 2;
@@ -1558,9 +1608,11 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
     CU(cudaMemcpyAsync(&n_tr, d_nt, sizeof(n_tr), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
-  for (int s = 0; s < n; s++) cnt[s] = hi[s] > topk ? topk + 1 : ex[s];
-  tkey.resize((size_t)n_tr); tval.resize((size_t)n_tr);
-  if (n_tr) {   // (slot, item) order on the device, then one copy each
+  out.surv_slot.clear(); out.surv_cnt.clear();
+  for (int c = 0; c < n_cand; c++)
+    if (cand_cnt[(size_t)c] <= topk) { out.surv_slot.push_back(cand[(size_t)c]); out.surv_cnt.push_back(cand_cnt[(size_t)c]); }
+  out.key = nullptr; out.val = nullptr; out.n_keys = 0;
+  if (n_tr) {   // (slot, item) order on the device, then one copy each into pinned host memory
     if (n_tr >= 0x7fffffffull) return fail(EALS_ERR_UNSUPPORTED, "too many ranking keys (%llu)", n_tr);
     OK(ws.tkey_out.reserve((size_t)n_tr)); OK(ws.tval_out.reserve((size_t)n_tr));
     size_t tmp = 0;
@@ -1571,9 +1623,13 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
     if (cub::DeviceRadixSort::SortPairs(ws.cub_tmp.p, tmp, ws.tkey.p, ws.tkey_out.p, ws.tval.p, ws.tval_out.p, (int)n_tr, 0, 32 + slot_bits, st) != cudaSuccess)
       return fail(EALS_ERR_CUDA, "ranking key sort");
     m->launches++;
-    CU(cudaMemcpyAsync(tkey.data(), ws.tkey_out.p, sizeof(unsigned long long) * n_tr, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(tval.data(), ws.tval_out.p, sizeof(int32_t) * n_tr, cudaMemcpyDeviceToHost, st));
+    OK(ws.host.reserve((size_t)n_tr * 12 + 64));
+    unsigned long long* hk = reinterpret_cast<unsigned long long*>(ws.host.p);
+    int32_t* hv = reinterpret_cast<int32_t*>(ws.host.p + (size_t)n_tr * 8);
+    CU(cudaMemcpyAsync(hk, ws.tkey_out.p, sizeof(unsigned long long) * n_tr, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hv, ws.tval_out.p, sizeof(int32_t) * n_tr, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    out.key = hk; out.val = hv; out.n_keys = (size_t)n_tr;
   }
   tm.lap("eval: counts + keys to host");
   if (getenv("EALS_VERBOSE") && getenv("EALS_VERBOSE")[0] == '1')
@@ -1597,53 +1653,58 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
   CU(cudaMemcpyAsync(ws.users.p, users_h.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
   eals::eval_gt_score_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->U, m->V, ws.gt.p, ws.users.p, 0, n, K, LD, ws.gts.p);
   OK(check_launch(m));
-  std::vector<int32_t> cnt((size_t)n, 0);
-  std::vector<unsigned long long> tkey;
-  std::vector<int32_t> tval;
+  ScanResult res;
   const bool want_triples = mode != EALS_EVAL_EXACT;
   const bool scalar_only = getenv("EALS_EVAL_SCALAR") && getenv("EALS_EVAL_SCALAR")[0] == '1';
   bool done = false;
   m->eval_engine = 0;
   if (n >= kTcMinUsers && K <= 256 && !scalar_only) {
     bool overflow = false;
-    OK(scan_tc(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tkey, tval, &overflow));
+    OK(scan_tc(m, n, ws.users.p, ws.gts.p, topk, want_triples, res, &overflow));
     done = !overflow;
     if (done) m->eval_engine = 1;
   }
-  if (!done) OK(scan_exact(m, n, ws.users.p, ws.gts.p, topk, want_triples, cnt, tkey, tval));
+  if (!done) OK(scan_exact(m, n, ws.users.p, ws.gts.p, topk, want_triples, res));
   StageTimer tm_host;
 
-  std::vector<int> pos((size_t)n, -1);
+  // Only the survivors can score; all other users get (0, 0, 0) and count_larger = topK + 1.
+  const size_t ns = res.surv_slot.size();
+  std::vector<int> pos(ns, -1);
   if (mode == EALS_EVAL_EXACT) {
-    for (int s = 0; s < n; s++)
-      if (cnt[s] < topk) pos[s] = cnt[s];
+    for (size_t t = 0; t < ns; t++)
+      if (res.surv_cnt[t] < topk) pos[t] = res.surv_cnt[t];
   } else {
-    // Replay of the reference's ranking for the survivors of the early-out (countLarger > topK -> zeros,
-    // MF_fastALS.cpp:633-634) with the real libstdc++ partial_sort_copy, the survivors spread over the host
-    // threads; a survivor's (item, key) stream is its range of the sorted key arrays.
-    std::vector<int32_t> surv;
-    for (int s = 0; s < n; s++)
-      if (cnt[s] <= topk) surv.push_back(s);
-    parallel_chunks((int64_t)surv.size(), nullptr, [&](int, int64_t b0, int64_t b1) {
+    // Replay of the reference's ranking (MF_fastALS.cpp:641-656) with the real libstdc++ partial_sort_copy,
+    // the survivors spread over the host threads; a survivor's (item, key) stream is its range of the sorted
+    // key arrays.
+    const unsigned long long* key = res.key;
+    const int32_t* val = res.val;
+    const size_t nk = res.n_keys;
+    parallel_chunks((int64_t)ns, nullptr, [&](int, int64_t b0, int64_t b1) {
       std::vector<std::pair<int, int>> nz;
       for (int64_t t = b0; t < b1; t++) {
-        const int s = surv[(size_t)t];
+        const int s = res.surv_slot[(size_t)t];
         const unsigned long long lo = (unsigned long long)(uint32_t)s << 32;
-        size_t q = (size_t)(std::lower_bound(tkey.begin(), tkey.end(), lo) - tkey.begin());
+        size_t q = nk ? (size_t)(std::lower_bound(key, key + nk, lo) - key) : 0;
         nz.clear();
-        for (; q < tkey.size() && (tkey[q] >> 32) == (unsigned long long)(uint32_t)s; q++)
-          nz.emplace_back((int)(tkey[q] & 0xffffffffu), tval[q]);
-        pos[(size_t)s] = reference_rank(nz, N, topk, gt_slot_h[s]);
+        for (; q < nk && (key[q] >> 32) == (unsigned long long)(uint32_t)s; q++)
+          nz.emplace_back((int)(key[q] & 0xffffffffu), val[q]);
+        pos[(size_t)t] = reference_rank(nz, N, topk, gt_slot_h[s]);
       }
     });
   }
-  for (int s = 0; s < n; s++) {
+  if (hr) std::fill(hr, hr + n, 0.0);
+  if (ndcg) std::fill(ndcg, ndcg + n, 0.0);
+  if (prec) std::fill(prec, prec + n, 0.0);
+  if (count_larger) std::fill(count_larger, count_larger + n, topk + 1);
+  for (size_t t = 0; t < ns; t++) {     // ascending slot: the same summation order as a loop over all users
+    const int s = res.surv_slot[t];
     double r0 = 0, r1 = 0, r2 = 0;
-    if (pos[s] >= 0) { r0 = 1; r1 = metric_ndcg(pos[s]); r2 = 1.0 / (pos[s] + 1); }
+    if (pos[t] >= 0) { r0 = 1; r1 = metric_ndcg(pos[t]); r2 = 1.0 / (pos[t] + 1); }
     if (hr) hr[s] = r0;
     if (ndcg) ndcg[s] = r1;
     if (prec) prec[s] = r2;
-    if (count_larger) count_larger[s] = std::min(cnt[s], topk + 1);
+    if (count_larger) count_larger[s] = res.surv_cnt[t];
     sums[0] += r0; sums[1] += r1; sums[2] += r2;
   }
   tm_host.lap("eval: host ranking replay + metrics");

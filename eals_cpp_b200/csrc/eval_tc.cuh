@@ -60,7 +60,10 @@ struct Cfg {
   static constexpr size_t kU = (size_t)UT * NKC * kChunk;
   static constexpr size_t kStage = (size_t)NKC * kChunk;
   static constexpr size_t kBar = 256;
+  static constexpr int kStagePairs = 448;                          // MODE 1: candidate pairs staged per epilogue warp
+  static constexpr size_t kEmit = 4 * (size_t)kStagePairs * 16;
   static constexpr size_t kSmem = 1024 + kU + S * kStage + kBar;   // 1024: alignment slack for the swizzle atoms
+  static constexpr size_t kSmemEmit = kSmem + kEmit;
   static constexpr int kTmemCols = 512;
 };
 
@@ -199,8 +202,18 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_act = *a.n_act;
-  const int n_works = (n_act + UT * kTM - 1) / (UT * kTM);
-  const int n_it = a.it1 - a.it0;
+  // Work item = (group of UT user tiles, chunk of the item-tile range).  With many user tiles a work item
+  // walks the whole range (chunks = 1: the user tiles are loaded once); when the working set has shrunk to a
+  // few tiles the range is cut so that every SM still gets ~4 work items (the candidate pass over 40k users
+  // of a 10M-user evaluation was two waves of 148 + 8 CTAs walking 15,625 tiles each before this).
+  const int n_uw = (n_act + UT * kTM - 1) / (UT * kTM);
+  const int n_it_all = a.it1 - a.it0;
+  int chunks = 1;
+  if (n_uw > 0 && n_uw < 4 * (int)gridDim.x) chunks = (4 * (int)gridDim.x + n_uw - 1) / n_uw;
+  chunks = max(1, min(chunks, (n_it_all + 15) / 16));
+  const int tpc = (n_it_all + chunks - 1) / chunks;
+  chunks = (n_it_all + tpc - 1) / tpc;
+  const int n_works = n_uw * chunks;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -208,19 +221,21 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
       int stage = 0;
       uint32_t phase = 0, uphase = 0;
       for (int w = blockIdx.x; w < n_works; w += gridDim.x) {
+        const int uw = w / chunks, tb = (w % chunks) * tpc, n_it = min(tpc, n_it_all - tb);
+        const int it_base = a.it0 + tb;
         mbar_wait(bar_uempty, uphase ^ 1);
         mbar_expect_tx(bar_ufull, (uint32_t)C::kU);
 #pragma unroll
         for (int j = 0; j < UT; j++)
 #pragma unroll
           for (int kc = 0; kc < NKC; kc++)
-            tma_load_2d(u_smem + (uint32_t)((j * NKC + kc) * kChunk), &mapU, kc * kKC, (w * UT + j) * kTM, bar_ufull);
+            tma_load_2d(u_smem + (uint32_t)((j * NKC + kc) * kChunk), &mapU, kc * kKC, (uw * UT + j) * kTM, bar_ufull);
         for (int t = 0; t < n_it; t++) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_full + 8 * stage, (uint32_t)C::kStage);
 #pragma unroll
           for (int kc = 0; kc < NKC; kc++)
-            tma_load_2d(v_smem + (uint32_t)(stage * C::kStage + kc * kChunk), &mapV, kc * kKC, (a.it0 + t) * kTN, bar_full + 8 * stage);
+            tma_load_2d(v_smem + (uint32_t)(stage * C::kStage + kc * kChunk), &mapV, kc * kKC, (it_base + t) * kTN, bar_full + 8 * stage);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
         uphase ^= 1;
@@ -232,6 +247,7 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
     int stage = 0, ab = 0;
     uint32_t phase = 0, uphase = 0, aphase = 0;
     for (int w = blockIdx.x; w < n_works; w += gridDim.x) {
+      const int n_it = min(tpc, n_it_all - (w % chunks) * tpc);
       mbar_wait(bar_ufull, uphase);
       tc_fence_after();
       for (int t = 0; t < n_it; t++) {
@@ -267,12 +283,28 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
     const int q = warp & 3;
     int ab = 0;
     uint32_t aphase = 0;
+    // MODE 1: this warp's staging buffer for candidate pairs (flushed to the global list with one atomic)
+    EvalPair* stage_buf = reinterpret_cast<EvalPair*>(smem_raw + (bars + (uint32_t)C::kBar - smem_u32(smem_raw))) + (warp - 2) * C::kStagePairs;
+    int fill = 0;
+    auto flush = [&]() {
+      __syncwarp();
+      if (fill > 0) {
+        unsigned long long fb = 0;
+        if (lane == 0) fb = atomicAdd(a.n_pairs, (unsigned long long)fill);
+        fb = __shfl_sync(kFullMask, fb, 0);
+        for (int i = lane; i < fill; i += 32)
+          if (fb + i < a.cap_pairs) a.pairs[fb + i] = stage_buf[i];
+      }
+      fill = 0;
+      __syncwarp();
+    };
     for (int w = blockIdx.x; w < n_works; w += gridDim.x) {
+      const int uw = w / chunks, tb = (w % chunks) * tpc, n_it = min(tpc, n_it_all - tb);
       float ghi[UT], glo[UT], na[UT], nd[UT], ns[UT], one[UT];
       int slot[UT], cnt[UT];
 #pragma unroll
       for (int j = 0; j < UT; j++) {
-        const int p = (w * UT + j) * kTM + q * 32 + lane;
+        const int p = (uw * UT + j) * kTM + q * 32 + lane;
         slot[j] = -1; cnt[j] = 0;
         ghi[j] = glo[j] = na[j] = nd[j] = ns[j] = one[j] = 0.f;
         if (p < n_act) {
@@ -282,7 +314,7 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
         }
       }
       for (int t = 0; t < n_it; t++) {
-        const int it = a.it0 + t;
+        const int it = a.it0 + tb + t;
         const float2 tn = __ldg(a.tile_norm + it);
         const int nvalid = a.n_items - it * kTN;      // < 128 only in the last tile
         mbar_wait(bar_accfull + 8 * ab, aphase);
@@ -324,8 +356,9 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
             }
           }
           if (MODE == 1) {
-            // Warp-aggregated append: one atomic per warp, tile and user tile instead of one per pair (a chain of
-            // ~700 dependent atomics per thread made this pass 1.9 s of a 5 s evaluation at 10M x 2M, r2d profile).
+            // Warp-aggregated append into this warp's shared-memory staging buffer; the buffer goes to the global
+            // list with ONE atomic per flush (one atomic per pair — ~700 dependent atomics per thread — made this
+            // pass 1.9 s of a 5 s evaluation at 10M x 2M; one per warp and tile still 0.26 s: profiles r2d / r2e).
             int mine = 0;
 #pragma unroll
             for (int c = 0; c < kTN / 32; c++) mine += __popc(m1[c] | m2[c]);
@@ -337,10 +370,14 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
             }
             const int total = __shfl_sync(kFullMask, incl, 31);
             if (total > 0) {
+              if (fill + total > C::kStagePairs) flush();
+              const bool direct = total > C::kStagePairs;          // more than the buffer holds: straight to the list
               unsigned long long wbase = 0;
-              if (lane == 0) wbase = atomicAdd(a.n_pairs, (unsigned long long)total);
-              wbase = __shfl_sync(kFullMask, wbase, 0);
-              unsigned long long pos = wbase + (unsigned long long)(incl - mine);
+              if (direct) {
+                if (lane == 0) wbase = atomicAdd(a.n_pairs, (unsigned long long)total);
+                wbase = __shfl_sync(kFullMask, wbase, 0);
+              }
+              int at = fill + incl - mine;
 #pragma unroll
               for (int c = 0; c < kTN / 32; c++) {
                 uint32_t any = m1[c] | m2[c];
@@ -348,10 +385,13 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
                   const int i = __ffs(any) - 1;
                   any &= any - 1;
                   const int fl = ((m1[c] >> i) & 1) | (((m2[c] >> i) & 1) << 1);
-                  if (pos < a.cap_pairs) a.pairs[pos] = EvalPair{slot[j], a.perm[it * kTN + c * 32 + i], fl, 0};
-                  pos++;
+                  const EvalPair pr{slot[j], a.perm[it * kTN + c * 32 + i], fl, 0};
+                  if (!direct) stage_buf[at] = pr;
+                  else if (wbase + (unsigned long long)(at - fill) < a.cap_pairs) a.pairs[wbase + (unsigned long long)(at - fill)] = pr;
+                  at++;
                 }
               }
+              if (!direct) fill += total;
             }
           }
         }
@@ -363,7 +403,12 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
       if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < UT; j++)
-          if (slot[j] >= 0 && cnt[j]) a.cnt_hi[slot[j]] += cnt[j];   // one thread per slot and launch: no atomics
+          if (slot[j] >= 0 && cnt[j]) {
+            if (chunks == 1) a.cnt_hi[slot[j]] += cnt[j];   // one thread per slot and launch
+            else atomicAdd(a.cnt_hi + slot[j], cnt[j]);     // several item chunks of the same users run concurrently
+          }
+      } else {
+        flush();
       }
     }
   }
