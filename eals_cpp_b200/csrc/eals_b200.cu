@@ -78,9 +78,9 @@ struct StageTimer {
 
 // Host-side helper: fn(thread, begin, end) over [0, n) in contiguous chunks on up to 16 threads.
 template <typename F>
-void parallel_chunks(int64_t n, int* n_threads_out, F fn) {
+void parallel_chunks(int64_t n, int* n_threads_out, F fn, int64_t min_per_thread = 65536) {
   unsigned hw = std::thread::hardware_concurrency();
-  int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, 16u)), std::max<int64_t>(1, n / 65536));
+  int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, 16u)), std::max<int64_t>(1, n / min_per_thread));
   if (n_threads_out) *n_threads_out = T;
   if (T <= 1) { fn(0, (int64_t)0, n); return; }
   std::vector<std::thread> th;
@@ -1567,7 +1567,7 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
   unsigned long long got = 0;
   unsigned long long* d_np = ws.counters.p + 1;
   if (n_cand > 0) {
-    unsigned long long cap = std::min<unsigned long long>(1ull << 27, std::max<unsigned long long>(1ull << 20, 512ull * (unsigned long long)n_cand));
+    unsigned long long cap = std::min<unsigned long long>(1ull << 27, std::max<unsigned long long>(1ull << 20, 1024ull * (unsigned long long)n_cand));
     if (const char* e = getenv("EALS_EVAL_PAIR_CAP")) cap = std::max<unsigned long long>(16, strtoull(e, nullptr, 10));
     unsigned long long hard_cap = 1ull << 30;           // 16 GB of pairs: beyond this the filter is not filtering
     if (const char* e = getenv("EALS_EVAL_PAIR_HARD_CAP")) hard_cap = strtoull(e, nullptr, 10);
@@ -1691,7 +1691,7 @@ int evaluate_slots(eals_model* m, const std::vector<int32_t>& users_h, const int
           nz.emplace_back((int)(key[q] & 0xffffffffu), val[q]);
         pos[(size_t)t] = reference_rank(nz, N, topk, gt_slot_h[s]);
       }
-    });
+    }, 256);
   }
   if (hr) std::fill(hr, hr + n, 0.0);
   if (ndcg) std::fill(ndcg, ndcg + n, 0.0);

@@ -27,13 +27,13 @@
 // are visited in order of decreasing norm: the tile maxima are tight and the high scorers come first, so
 // most users are decided in the first item block and leave the working set.
 //
-// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
 //   warp 0      TMA producer: the UT user tiles of a work item once, then the item tiles through an
 //               S-stage shared-memory ring (cp.async.bulk.tensor, 128-byte swizzle, mbarrier tx counts)
 //   warp 1      tcgen05.mma issuer (one lane): per stage UT x (KP/16) MMAs of 128 x 128 x 16 into one of
 //               two TMEM accumulator buffers; tcgen05.commit releases the stage and publishes the buffer
-//   warps 2-5   epilogue: tcgen05.ld of the warp's 32 TMEM lanes (= 32 users), compare against the
-//               per-(user, tile) thresholds, count in registers (MODE 0) or emit candidates (MODE 1)
+//   warps 2-9   epilogue: tcgen05.ld of the warp's 32 TMEM lanes (= 32 users) x 64 columns, compare against
+//               the per-(user, tile) thresholds, count in registers (MODE 0) or emit candidates (MODE 1)
 // Two user tiles share every staged item tile (UT = 2 for K <= 128): 32 bytes of L2 traffic per SM and
 // clock instead of 64, which is what keeps 148 SMs under the L2 fabric's ~6300 B/clk.  The host walks
 // the catalogue in L2-sized item blocks and compacts the working set between them on the device.
@@ -51,7 +51,7 @@ constexpr int kTM = 128;             // users per accumulator tile (UMMA M)
 constexpr int kTN = 128;             // items per stage (UMMA N)
 constexpr int kKC = 64;              // halves per 128-byte swizzle row
 constexpr int kChunk = 128 * 128;    // bytes of one [128 rows][64 halves] swizzled sub-tile
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;           // TMA warp + MMA warp + 8 epilogue warps
 
 template <int NKC>
 struct Cfg {
@@ -60,8 +60,8 @@ struct Cfg {
   static constexpr size_t kU = (size_t)UT * NKC * kChunk;
   static constexpr size_t kStage = (size_t)NKC * kChunk;
   static constexpr size_t kBar = 256;
-  static constexpr int kStagePairs = 448;                          // MODE 1: candidate pairs staged per epilogue warp
-  static constexpr size_t kEmit = 4 * (size_t)kStagePairs * 16;
+  static constexpr int kStagePairs = 224;                          // MODE 1: candidate pairs staged per epilogue warp
+  static constexpr size_t kEmit = 8 * (size_t)kStagePairs * 16;
   static constexpr size_t kSmem = 1024 + kU + S * kStage + kBar;   // 1024: alignment slack for the swizzle atoms
   static constexpr size_t kSmemEmit = kSmem + kEmit;
   static constexpr int kTmemCols = 512;
@@ -132,22 +132,21 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (base lane + t).
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets TMEM lane (base lane + t).  The values
+// may only be read after tc_ld_wait().
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, float (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+        "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+        "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr)
+      : "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major, 128-byte-swizzled operand tile (rows of 64 halves, 8-row
 // groups 1024 bytes apart): start address >> 4 | LBO = 1 (ignored for swizzled K-major) | SBO = 1024 >> 4 |
@@ -188,7 +187,7 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_ufull, 1); mbar_init(bar_uempty, 1);
-    for (int b = 0; b < 2; b++) { mbar_init(bar_accfull + 8 * b, 1); mbar_init(bar_accempty + 8 * b, 4); }
+    for (int b = 0; b < 2; b++) { mbar_init(bar_accfull + 8 * b, 1); mbar_init(bar_accempty + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
@@ -279,8 +278,12 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
       uphase ^= 1;
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32 (warp & 3) .. +31 =====
-    const int q = warp & 3;
+    // ===== epilogue: warps 2..9.  TMEM lane quadrant q = warp & 3 (a warp may only touch lanes 32 q .. 32 q + 31 =
+    // 32 users), column half hf = (warp - 2) >> 2 (64 of the 128 items of a tile).  Eight warps, two per scheduler,
+    // and both TMEM loads of a (tile, user tile) in flight before the first wait: with four warps and a wait after
+    // every load the compare loop, not the tensor pipe, set the pace (2.7k cycles per tile against 1k; r2f). =====
+    const int q = warp & 3, hf = (warp - 2) >> 2;
+    constexpr int kCols = kTN / 2;                       // columns per epilogue warp
     int ab = 0;
     uint32_t aphase = 0;
     // MODE 1: this warp's staging buffer for candidate pairs (flushed to the global list with one atomic)
@@ -316,7 +319,7 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
       for (int t = 0; t < n_it; t++) {
         const int it = a.it0 + tb + t;
         const float2 tn = __ldg(a.tile_norm + it);
-        const int nvalid = a.n_items - it * kTN;      // < 128 only in the last tile
+        const int nvalid = a.n_items - it * kTN - hf * kCols;      // valid columns of this warp's half (< 64 only at the end)
         mbar_wait(bar_accfull + 8 * ab, aphase);
         tc_fence_after();
 #pragma unroll
@@ -326,42 +329,39 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
           const float thr_hi = slot[j] >= 0 ? __fadd_ru(ghi[j], E) : __int_as_float(0x7f800000);
           const float thr_lo = __fsub_rd(glo[j], E);
           const float thr_one = __fsub_rd(one[j], E);
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * UT + j) * kTN);
-          uint32_t m1[kTN / 32], m2[kTN / 32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * UT + j) * kTN + hf * kCols);
+          float v[kCols];
+          tc_ld32_issue(taddr, *reinterpret_cast<float(*)[32]>(&v[0]));
+          tc_ld32_issue(taddr + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+          tc_ld_wait();
+          if (MODE == 0) {
+            if (nvalid >= kCols) {
 #pragma unroll
-          for (int c = 0; c < kTN / 32; c++) {
-            m1[c] = m2[c] = 0;
-            float v[32];
-            tc_ld32(taddr + c * 32, v);
-            if (MODE == 0) {
-              if (nvalid >= kTN) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) cnt[j] += v[i] > thr_hi ? 1 : 0;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; i++) cnt[j] += (c * 32 + i < nvalid && v[i] > thr_hi) ? 1 : 0;
-              }
+              for (int i = 0; i < kCols; i++) cnt[j] += v[i] > thr_hi ? 1 : 0;
             } else {
-              // candidate masks of this 32-column chunk: bit i of m1 = "may exceed the gt score", of m2 = "|score| may reach 1"
+#pragma unroll
+              for (int i = 0; i < kCols; i++) cnt[j] += (i < nvalid && v[i] > thr_hi) ? 1 : 0;
+            }
+          } else {
+            // candidate masks: bit i of m1 = "may exceed the gt score", of m2 = "|score| may reach 1"
+            uint32_t m1[2], m2[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
               uint32_t b1 = 0, b2 = 0;
 #pragma unroll
               for (int i = 0; i < 32; i++) {
-                b1 |= (v[i] >= thr_lo ? 1u : 0u) << i;
-                b2 |= (fabsf(v[i]) >= thr_one ? 1u : 0u) << i;
+                b1 |= (v[c * 32 + i] >= thr_lo ? 1u : 0u) << i;
+                b2 |= (fabsf(v[c * 32 + i]) >= thr_one ? 1u : 0u) << i;
               }
               const int lim = nvalid - c * 32;
               const uint32_t live = slot[j] < 0 || lim <= 0 ? 0u : (lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u));
               m1[c] = b1 & live;
               m2[c] = b2 & live;
             }
-          }
-          if (MODE == 1) {
             // Warp-aggregated append into this warp's shared-memory staging buffer; the buffer goes to the global
             // list with ONE atomic per flush (one atomic per pair — ~700 dependent atomics per thread — made this
             // pass 1.9 s of a 5 s evaluation at 10M x 2M; one per warp and tile still 0.26 s: profiles r2d / r2e).
-            int mine = 0;
-#pragma unroll
-            for (int c = 0; c < kTN / 32; c++) mine += __popc(m1[c] | m2[c]);
+            const int mine = __popc(m1[0] | m2[0]) + __popc(m1[1] | m2[1]);
             int incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -379,13 +379,13 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
               }
               int at = fill + incl - mine;
 #pragma unroll
-              for (int c = 0; c < kTN / 32; c++) {
+              for (int c = 0; c < 2; c++) {
                 uint32_t any = m1[c] | m2[c];
                 while (any) {
                   const int i = __ffs(any) - 1;
                   any &= any - 1;
                   const int fl = ((m1[c] >> i) & 1) | (((m2[c] >> i) & 1) << 1);
-                  const EvalPair pr{slot[j], a.perm[it * kTN + c * 32 + i], fl, 0};
+                  const EvalPair pr{slot[j], a.perm[it * kTN + hf * kCols + c * 32 + i], fl, 0};
                   if (!direct) stage_buf[at] = pr;
                   else if (wbase + (unsigned long long)(at - fill) < a.cap_pairs) a.pairs[wbase + (unsigned long long)(at - fill)] = pr;
                   at++;
@@ -403,10 +403,7 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
       if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < UT; j++)
-          if (slot[j] >= 0 && cnt[j]) {
-            if (chunks == 1) a.cnt_hi[slot[j]] += cnt[j];   // one thread per slot and launch
-            else atomicAdd(a.cnt_hi + slot[j], cnt[j]);     // several item chunks of the same users run concurrently
-          }
+          if (slot[j] >= 0 && cnt[j]) atomicAdd(a.cnt_hi + slot[j], cnt[j]);   // two column halves (and item chunks) per slot
       } else {
         flush();
       }

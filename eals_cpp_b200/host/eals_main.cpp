@@ -11,7 +11,11 @@
 //   4. build the model, run maxIter iterations, evaluate (main.cpp:227-231).
 // Unlike the reference it takes real arguments:
 //   eals_main [--data yelp.rating] [--factors 64] [--iters 20] [--w0 10] [--alpha 0.75] [--reg 0.01]
-//             [--topk 10] [--no-loss] [--exact-eval] [--device 0] [--online U,I]
+//             [--topk 10] [--no-loss] [--exact-eval] [--device 0] [--gpus N | --devices 0,1,..] [--online U,I]
+//             [--save FILE] [--load FILE]
+// --gpus N: shard users and items over GPUs device .. device+N-1 (eals_group: the exchange runs inside the
+// library); --devices lists them explicitly — a repeated id puts several ranks on one GPU.
+// --save / --load: factor checkpoint after training / instead of the random initialisation.
 // --online U,I: after training and evaluation, add the interaction (U, I) with the online update
 // (updateModel, MF_fastALS.cpp:223-242) and print the prediction before and after.
 #include <algorithm>
@@ -23,6 +27,7 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <vector>
 
 #include "MF_fastALS.h"
 #include "eals_host_types.h"
@@ -38,7 +43,9 @@ int main(int argc, char** argv) {
   double w0 = 10, reg = 0.01, alpha = 0.75, init_mean = 0, init_stdev = 0.01;
   int factors = 64, maxIter = 20, topK = 10, threadNum = 1, device = 0;
   bool showProgress = false, showLoss = true, exact = false;
-  int online_u = -1, online_i = -1;
+  int online_u = -1, online_i = -1, n_gpus = 1;
+  std::vector<int> devices;
+  std::string save_path, load_path;
   for (int a = 1; a < argc; a++) {
     auto is = [&](const char* f) { return std::strcmp(argv[a], f) == 0; };
     auto next = [&]() -> const char* { if (a + 1 >= argc) { std::fprintf(stderr, "missing value after %s\n", argv[a]); std::exit(2); } return argv[++a]; };
@@ -50,6 +57,10 @@ int main(int argc, char** argv) {
     else if (is("--reg")) reg = std::atof(next());
     else if (is("--topk")) topK = std::atoi(next());
     else if (is("--device")) device = std::atoi(next());
+    else if (is("--gpus")) n_gpus = std::max(1, std::atoi(next()));
+    else if (is("--devices")) { std::istringstream in(next()); for (std::string t; std::getline(in, t, ',');) devices.push_back(std::atoi(t.c_str())); }
+    else if (is("--save")) save_path = next();
+    else if (is("--load")) load_path = next();
     else if (is("--no-loss")) showLoss = false;
     else if (is("--exact-eval")) exact = true;
     else if (is("--online")) { if (std::sscanf(next(), "%d,%d", &online_u, &online_i) != 2) { std::fprintf(stderr, "--online wants U,I\n"); return 2; } }
@@ -103,10 +114,15 @@ int main(int argc, char** argv) {
   if ((int)testRatings.size() != userCount) { std::fprintf(stderr, "every user needs at least one rating\n"); return EXIT_FAILURE; }
 
   try {
+    if (!devices.empty()) n_gpus = (int)devices.size();
     Model fals(trainMatrix, testRatings, topK, threadNum, factors, maxIter, w0, alpha, reg, init_mean,
-               init_stdev, showProgress, showLoss, userCount, itemCount, device);
+               init_stdev, showProgress, showLoss, userCount, itemCount, device, n_gpus,
+               devices.empty() ? nullptr : devices.data());
+    if (!load_path.empty()) fals.load(load_path);
     std::cout << "Start building model" << std::endl;
     fals.buildModel();
+    if (!save_path.empty()) fals.save(save_path);
+    if (n_gpus > 1) std::cerr << "replicas consistent: " << (fals.replicas_consistent() ? "yes" : "NO") << std::endl;
     std::vector<double> res = fals.evaluate(exact);
     std::cout << "<hr, ndcg, prec>: \t" << res[0] << "\t" << res[1] << "\t" << res[2] << std::endl;
     if (online_u >= 0) {

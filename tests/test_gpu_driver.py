@@ -32,7 +32,11 @@ def _ratings(path, M=120, N=80, seed=4):
     return split
 
 
-def test_cpp_driver_trains_evaluates_and_updates_online(tmp_path):
+@pytest.mark.parametrize("devices", [None, "0,0,0"])
+def test_cpp_driver_trains_evaluates_and_updates_online(tmp_path, devices):
+    """devices=None: one GPU.  "0,0,0": the C++ class drives THREE ranks (eals_group; here all on GPU 0, on a
+    multi-GPU box `--gpus N` spreads them) — users and items sharded, the exchange inside the library — and must
+    print the same losses, metrics and online update."""
     from eals_cpp_b200 import build
     from oracle.bindings import PortModel, csr_to_csc
     exe = build.build_host_example()
@@ -41,10 +45,16 @@ def test_cpp_driver_trains_evaluates_and_updates_online(tmp_path):
     M = len(split)
     N = 1 + max(max(t + [g]) for t, g in split)
     K, iters = 8, 3
-    res = subprocess.run([exe, "--data", str(data), "--factors", str(K), "--iters", str(iters), "--online", "3,5"],
-                         capture_output=True, text=True, timeout=300)
+    ckpt = tmp_path / "factors.eals"
+    cmd = [exe, "--data", str(data), "--factors", str(K), "--iters", str(iters), "--online", "3,5", "--save", str(ckpt)]
+    if devices:
+        cmd += ["--devices", devices]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = res.stdout
+    if devices:
+        assert "replicas consistent: yes" in res.stderr
+    assert os.path.getsize(ckpt) == 32 + 8 * (M * K + N * K + N)
     assert f"#Users\t{M}" in out and f"#items\t{N}" in out          # main.cpp:212-216 lines
     losses = [float(x) for x in re.findall(r"Iter=\d+ \S+ [-+] loss:(\S+)", out)]
     assert len(losses) == iters
