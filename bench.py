@@ -537,12 +537,24 @@ def main():
                 configs[name] = {"workload": workload_string(name, sp2, sm2.nnz), "epoch_ms": ms2,
                                  "value": 2.0 * sm2.nnz * sp2["K"] / (ms2 * 1e-3), "unit": UNIT, "sweep_ms": sw2,
                                  "hbm_frac": by2 / (sw2 * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                 "fits_l2": by2 < 126e6 * 8, "loss_after": f2.loss(), "epochs_timed": n_ep}
+                                 "working_set_fits_l2": (sp2["M"] + sp2["N"]) * sp2["K"] * 8 + sm2.nnz * 8 < 126e6, "loss_after": f2.loss(), "epochs_timed": n_ep}
                 f2.close()
                 del f2, sm2
                 torch.cuda.empty_cache()
             except Exception as e:       # a side measurement must never take the headline down with it
                 configs[name] = {"error": repr(e)}
+
+    if configs is not None and world == 1 and args.workload in ("c4", "c4s"):
+        # the reference's own factor initialisation at this scale (DenseMat.cpp:54-62: one sequential libstdc++ stream;
+        # ours is the same stream generated in parallel by LCG skip-ahead, bit-identical) — LAST, it overwrites the factors
+        try:
+            t0 = time.perf_counter()
+            stream_s = fals.init_factors()
+            configs["c4_init_factors"] = {"seconds": time.perf_counter() - t0, "host_stream_seconds": stream_s,
+                                          "values": max(M, N) * K, "host_threads": min(32, os.cpu_count() or 1),
+                                          "what": "eals_init_factors: libstdc++ minstd_rand0 + polar normal stream, bit-identical to the reference, + upload + initS"}
+        except Exception as e:
+            configs["c4_init_factors"] = {"error": repr(e)}
 
     if rank == 0:
         line = {

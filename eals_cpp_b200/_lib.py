@@ -48,6 +48,8 @@ SIGNATURES = {
     "eals_destroy": (C.c_int, [_P]),
     "eals_set_train": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "eals_init_factors": (C.c_int, [_P]),
+    "eals_debug_init_stream": (C.c_int, [C.c_double, C.c_double, _P, C.c_int64]),
+    "eals_init_seconds": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "eals_set_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
     "eals_get_factors": (C.c_int, [_P, C.c_int32, _P, _P]),
     "eals_save_factors": (C.c_int, [_P, C.c_char_p]),

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <random>
 #include <string>
@@ -197,6 +198,7 @@ struct eals_model {
   struct eals_eval_ws* eval = nullptr;   // evaluation workspace (grow-only)
   int eval_engine = 0;                   // engine of the last evaluate: 0 exact fp64 tiles, 1 tcgen05 filter + exact re-score
   long long eval_candidates = 0, eval_pairs = 0;
+  double init_stream_s = 0;              // host seconds of the last factor-stream generation
   bool su_fresh = true;          // SU describes the current U (false after single-row user updates without a Gram)
   double* S_tmp = nullptr;       // [LD][LD] scratch Gram for loss() while SU is stale
   int* flags = nullptr;          // [8] device scratch for validation kernels (no malloc/free per call)
@@ -755,6 +757,73 @@ int build_side(eals_model* m, Side& s, int begin, int end, int other_dim, int sp
   tm.lap("side: heavy units + upload");
   CU(cudaStreamSynchronize(m->stream));
   return EALS_OK;
+}
+
+// ---- the reference's factor initialisation, in parallel, bit for bit ---------------------------------------
+// DenseMat::init (DenseMat.cpp:54-62) draws rows*cols values from std::normal_distribution<double> over a
+// default-constructed std::default_random_engine = minstd_rand0 (x' = 16807 x mod 2^31-1, seed 1).  libstdc++'s
+// normal_distribution is Marsaglia's polar method (random.tcc:1811-1847): an ATTEMPT draws two uniforms
+// (generate_canonical<double,53> = two engine draws each, random.tcc:3349-3381), is rejected unless
+// 0 < x^2 + y^2 <= 1, and an accepted attempt yields two values (y*mult first, x*mult on the next call).  Every
+// attempt consumes exactly four engine draws whether accepted or not, so attempt j starts at stream position
+// 4j — reachable directly, the LCG has an O(log n) skip-ahead (a^n mod m).  The attempt stream is cut into
+// chunks; pass 1 counts the accepted attempts of every chunk (the same two generate_canonical calls and the same
+// test, no log / sqrt), a prefix sum gives every chunk its output offset, pass 2 runs the REAL
+// std::normal_distribution over an engine positioned at the chunk's first attempt for exactly the counted number
+// of values.  Same libm, same instantiations as the sequential loop — same bits (tested against the oracle),
+// seconds instead of tens of seconds at 10M x 128.
+uint64_t minstd0_state_after(uint64_t draws) {
+  const uint64_t mod = 2147483647ull;
+  uint64_t result = 1, base = 16807ull;      // seed 1 (random.h:1592-1593, 1641)
+  while (draws) {
+    if (draws & 1) result = result * base % mod;
+    base = base * base % mod;
+    draws >>= 1;
+  }
+  return result;                              // = 16807^draws mod m: the engine state after `draws` draws from seed 1
+}
+
+void init_stream(double mean, double stdev, double* out, size_t n) {
+  size_t chunk = 1 << 16;                     // attempts per chunk
+  if (const char* e = getenv("EALS_INIT_CHUNK")) chunk = std::max<size_t>(8, strtoull(e, nullptr, 10));
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t T = std::min<size_t>(hw, 32);
+  size_t produced = 0, first_chunk = 0;
+  while (produced < n) {
+    // a wave of chunks that will almost surely cover what is left (acceptance rate pi/4), at least one per thread
+    const size_t left_attempts = (size_t)((double)(n - produced) / 2.0 / 0.78) + 64;
+    const size_t wave = std::max<size_t>(1, std::min<size_t>((left_attempts + chunk - 1) / chunk, T * 64));
+    std::vector<size_t> acc(wave, 0);
+    auto over_chunks = [&](auto fn) {
+      std::vector<std::thread> th;
+      const size_t nt = std::min(T, wave);
+      for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&, t] { for (size_t c = t; c < wave; c += nt) fn(c); });
+      for (auto& x : th) x.join();
+    };
+    over_chunks([&](size_t c) {               // pass 1: accepted attempts of chunk c
+      std::minstd_rand0 eng((std::minstd_rand0::result_type)minstd0_state_after(4 * (first_chunk + c) * (uint64_t)chunk));
+      size_t a = 0;
+      for (size_t j = 0; j < chunk; j++) {
+        const double x = 2.0 * std::generate_canonical<double, std::numeric_limits<double>::digits>(eng) - 1.0;
+        const double y = 2.0 * std::generate_canonical<double, std::numeric_limits<double>::digits>(eng) - 1.0;
+        const double r2 = x * x + y * y;
+        a += !(r2 > 1.0 || r2 == 0.0);
+      }
+      acc[c] = a;
+    });
+    std::vector<size_t> off(wave + 1, produced);
+    for (size_t c = 0; c < wave; c++) off[c + 1] = off[c] + 2 * acc[c];
+    over_chunks([&](size_t c) {               // pass 2: the real distribution over the chunk's own engine
+      if (off[c] >= n) return;
+      std::minstd_rand0 eng((std::minstd_rand0::result_type)minstd0_state_after(4 * (first_chunk + c) * (uint64_t)chunk));
+      std::normal_distribution<double> distribution(mean, stdev);
+      const size_t end = std::min(n, off[c + 1]);
+      for (size_t t = off[c]; t < end; t++) out[t] = distribution(eng);
+    });
+    produced = std::min(n, off[wave]);
+    first_chunk += wave;
+  }
 }
 
 // Wi — MF_fastALS.cpp:55-72, on the host with the same libm pow and the same summation order.
@@ -1850,7 +1919,7 @@ int eals_init_factors(eals_model* m) {
   if (!m) return fail(EALS_ERR_ARG, "null model");
   CU(cudaSetDevice(m->p.device));
   // DenseMat::init (DenseMat.cpp:54-62): a fresh default-seeded engine per matrix, so U and V are
-  // prefixes of ONE stream; generated once with the very std:: classes the reference uses.
+  // prefixes of ONE stream; generated once, bit-identical to the reference's sequential loop (init_stream).
   const size_t rows = (size_t)std::max(m->M, m->N);
   std::vector<double> stream;
   try {
@@ -1858,9 +1927,9 @@ int eals_init_factors(eals_model* m) {
   } catch (const std::bad_alloc&) {
     return fail(EALS_ERR_ALLOC, "host allocation of the init stream failed");
   }
-  std::default_random_engine generator;
-  std::normal_distribution<double> distribution(m->p.init_mean, m->p.init_stdev);
-  for (size_t t = 0; t < stream.size(); t++) stream[t] = distribution(generator);
+  const auto t_init0 = std::chrono::steady_clock::now();
+  init_stream(m->p.init_mean, m->p.init_stdev, stream.data(), stream.size());
+  m->init_stream_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init0).count();
   OK(upload_dense(m, m->U, stream.data(), (size_t)m->M, EALS_HOST));
   OK(upload_dense(m, m->V, stream.data(), (size_t)m->N, EALS_HOST));
   CU(cudaStreamSynchronize(m->stream));
@@ -2137,6 +2206,18 @@ int eals_evaluate_user(eals_model* m, int32_t u, int32_t gt_item, int32_t topk, 
   CU(cudaSetDevice(m->p.device));
   std::vector<int32_t> users(1, u);
   return evaluate_slots(m, users, &gt_item, topk, mode, out, nullptr, nullptr, nullptr, nullptr);
+}
+
+int eals_debug_init_stream(double mean, double stdev, double* out, int64_t n) {
+  if (!out || n < 0) return fail(EALS_ERR_ARG, "bad argument");
+  init_stream(mean, stdev, out, (size_t)n);
+  return EALS_OK;
+}
+
+int eals_init_seconds(eals_model* m, double* host_stream_seconds) {
+  if (!m || !host_stream_seconds) return fail(EALS_ERR_ARG, "null argument");
+  *host_stream_seconds = m->init_stream_s;
+  return EALS_OK;
 }
 
 int eals_eval_stats(eals_model* m, int64_t out[3]) {

@@ -660,6 +660,14 @@ class MF_fastALS:
             return res, hr, ndcg, prec, cnt
         return res
 
+    def init_factors(self):
+        """U.init / V.init / initS again (MF_fastALS.cpp:85-90); returns the host seconds of the stream generation."""
+        check(self.lib.eals_init_factors(self.h))
+        self._replicas_written()
+        v = C.c_double()
+        check(self.lib.eals_init_seconds(self.h, C.byref(v)))
+        return v.value
+
     def eval_stats(self):
         """Engine of the last evaluate(): 'tcgen05' (fp16 tensor-core filter + exact fp64 re-score of the close
         calls) or 'fp64' (exact tile scan), the number of candidate users and of re-scored pairs."""

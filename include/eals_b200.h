@@ -127,6 +127,11 @@ int eals_set_train(eals_model* m, int32_t input_space, const int64_t* row_ptr,
  * default-seeded libstdc++ minstd_rand0 + polar normal stream, the SAME stream for U and V, then
  * both S caches. */
 int eals_init_factors(eals_model* m);
+/* Host seconds the last eals_init_factors spent generating the normal stream (parallel skip-ahead over the
+ * reference's LCG, bit-identical to the sequential loop). */
+int eals_init_seconds(eals_model* m, double* host_stream_seconds);
+/* The stream alone into a host array (no device needed): what eals_init_factors uploads. */
+int eals_debug_init_stream(double mean, double stdev, double* out, int64_t n);
 
 /* MF_fastALS::setUV (MF_fastALS.cpp:106-110), working: dense row-major [n][factors] fp64 in the
  * given space; either pointer may be NULL to keep that side.  Refreshes the S caches (initS). */

@@ -131,3 +131,25 @@ def test_empty_rows_keep_initial_factors(port):
     assert np.array_equal(m.U[[0, 2]], U0[[0, 2]]) and np.array_equal(m.V[3], V0[3])
     assert not np.array_equal(m.U[1], U0[1])
     assert m.Wi[3] == 0.0
+
+
+def test_parallel_init_stream_is_the_sequential_stream(monkeypatch):
+    """eals_init_factors generates the reference's normal stream in parallel chunks (LCG skip-ahead + the real
+    std::normal_distribution per chunk).  Exercised WITHOUT a GPU through the stand-alone export
+    eals_debug_init_stream: several chunk sizes, lengths that end inside a chunk and inside a pair, against the
+    oracle's sequential loop (itself pinned to the compiled reference above)."""
+    import ctypes as C
+    from eals_cpp_b200 import _lib
+    from oracle.bindings import Port
+    lib = _lib.load()
+    port = Port()
+    for chunk, n in ((8, 1), (8, 2), (8, 37), (64, 4096), (1000, 250_001), (1 << 16, 400_000)):
+        monkeypatch.setenv("EALS_INIT_CHUNK", str(chunk))
+        out = np.empty(n)
+        assert lib.eals_debug_init_stream(C.c_double(0.0), C.c_double(0.01), out.ctypes.data_as(C.c_void_p), C.c_int64(n)) == 0
+        want = port.normal_fill(n, 0.0, 0.01)
+        assert np.array_equal(out, want), (chunk, n)
+    monkeypatch.setenv("EALS_INIT_CHUNK", "4096")
+    out = np.empty(100_003)
+    lib.eals_debug_init_stream(C.c_double(1.5), C.c_double(2.0), out.ctypes.data_as(C.c_void_p), C.c_int64(len(out)))
+    assert np.array_equal(out, port.normal_fill(len(out), 1.5, 2.0))
