@@ -226,6 +226,9 @@ struct eals_model {
   size_t cap_full_rp = 0, cap_full_cp = 0, cap_full_ci = 0, cap_full_ri = 0, cap_route_tmp = 0;
   eals::PcOut out_to_items = {}, out_to_users = {};   // where the other side's caches live (all ranks)
   int n_ranks = 1, rank = 0;
+  cudaStream_t side_stream = nullptr;   // routing of the final predictions runs here, under the Gram
+  cudaEvent_t ev_swept = nullptr, ev_routed = nullptr;
+  bool route_pending = false;
   bool local_peers = false;      // peers are plain pointers of models in this process (eals_group), not CUDA IPC mappings
   bool pc_attached = false;      // caches usable: single rank, or both peers' cache sets mapped
   bool pc_users_attached = false, pc_items_attached = false;
@@ -1020,8 +1023,19 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   return EALS_OK;
 }
 
+// The routing copy of the previous sweep (side stream) must be complete before anything that follows on the
+// model's stream is allowed to mean "this half-epoch is done".
+int join_route(eals_model* m) {
+  if (m->route_pending) {
+    CU(cudaStreamWaitEvent(m->stream, m->ev_routed, 0));
+    m->route_pending = false;
+  }
+  return EALS_OK;
+}
+
 int sweep(eals_model* m, bool user, int only_row) {
   if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised (eals_init_factors / eals_set_factors)");
+  OK(join_route(m));
   Side& s = user ? m->users : m->items;
   CdSide a;
   a.ptr = s.ptr; a.idx = s.idx; a.val = s.val;
@@ -1052,10 +1066,30 @@ int sweep(eals_model* m, bool user, int only_row) {
   }
   if (user) { DISPATCH_LD(m->LD, OK((launch_cd<LD, true>(m, s, a, only_row)))); }
   else      { DISPATCH_LD(m->LD, OK((launch_cd<LD, false>(m, s, a, only_row)))); }
-  if (a.pc_stage && s.nnz > 0) {   // second phase: staged predictions to their owners, in destination order
-    eals::pc_route_kernel<<<(unsigned)((s.nnz + 255) / 256), 256, 0, m->stream>>>(
+  if (a.pc_stage && s.nnz > 0) {
+    // Second phase: staged predictions to their owners, in destination order.  Nobody needs them before the
+    // NEXT half-epoch's sweep, so the copy runs on a side stream under this half-epoch's Gram kernel and is
+    // joined at the end of gram() — i.e. before the all-reduce that orders the ranks (round 1 had it on the
+    // sweep's stream: 7 % of the step at 2 GPUs).
+    static const bool inline_route = getenv("EALS_ROUTE_INLINE") && getenv("EALS_ROUTE_INLINE")[0] == '1';
+    cudaStream_t rs = m->stream;
+    if (!inline_route) {
+      if (!m->side_stream) {
+        CU(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&m->ev_swept, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->ev_routed, cudaEventDisableTiming));
+      }
+      CU(cudaEventRecord(m->ev_swept, m->stream));
+      CU(cudaStreamWaitEvent(m->side_stream, m->ev_swept, 0));
+      rs = m->side_stream;
+    }
+    eals::pc_route_kernel<<<(unsigned)((s.nnz + 255) / 256), 256, 0, rs>>>(
         a.pc_stage, user ? m->route_src_u : m->route_src_i, user ? m->route_dst_u : m->route_dst_i, s.nnz, a.pc_out);
     OK(check_launch(m));
+    if (!inline_route) {
+      CU(cudaEventRecord(m->ev_routed, m->side_stream));
+      m->route_pending = true;
+    }
   }
   return sync_if_debug(m);
 }
@@ -1081,6 +1115,7 @@ int gram(eals_model* m, bool user, bool full) {
   double* S = user ? m->SU : m->SV;
   DISPATCH_LD(m->LD, OK(launch_gram<LD>(m, X, w, r0, r1, S)));
   if (user) m->su_fresh = true;
+  OK(join_route(m));
   return sync_if_debug(m);
 }
 
@@ -1818,6 +1853,7 @@ int eals_destroy(eals_model* m) {
   cudaFree(m->full_rp); cudaFree(m->full_cp); cudaFree(m->full_ci); cudaFree(m->full_ri); cudaFree(m->route_tmp);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
+  if (m->side_stream) { cudaStreamSynchronize(m->side_stream); cudaStreamDestroy(m->side_stream); cudaEventDestroy(m->ev_swept); cudaEventDestroy(m->ev_routed); }
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
   return EALS_OK;
@@ -2258,6 +2294,7 @@ int eals_stream(eals_model* m, void** cuda_stream) {
 int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own) {
   if (!m) return fail(EALS_ERR_ARG, "null model");
   CU(cudaSetDevice(m->p.device));
+  OK(join_route(m));
   CU(cudaStreamSynchronize(m->stream));
   fold_timings(m);
   m->stream = restore_own ? m->own_stream : (cudaStream_t)cuda_stream;
@@ -2372,6 +2409,7 @@ int eals_factor_hash(eals_model* m, uint64_t out[2]) {
 int eals_sync(eals_model* m) {
   if (!m) return fail(EALS_ERR_ARG, "null model");
   CU(cudaSetDevice(m->p.device));
+  OK(join_route(m));
   CU(cudaStreamSynchronize(m->stream));
   CU(cudaGetLastError());
   return EALS_OK;

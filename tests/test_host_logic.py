@@ -191,3 +191,23 @@ def test_update_model_host_flow_with_a_mocked_library():
     assert [c[0] for c in calls] == ["user", "item"] * 10
     with pytest.raises(IndexError):
         f.updateModel(M, 0)
+
+
+def test_cost_partition_is_contiguous_complete_and_balances_cost():
+    """eals_partition (used by eals_group and by the one-process-per-GPU path): bounds are monotone, cover every
+    row, give every rank at least one row, and balance the per-row cost model rather than raw nonzeros."""
+    from eals_cpp_b200.model import partition_by_cost, partition_by_nnz
+    rng = np.random.default_rng(5)
+    lens = np.concatenate([rng.integers(1, 30, 5000), rng.integers(600, 5000, 40), rng.integers(1, 30, 5000)])
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        b = partition_by_cost(ptr, world)
+        assert b[0] == 0 and b[-1] == len(lens) and all(b[i] < b[i + 1] for i in range(world))
+        cost = np.where(lens <= 32, 13.0, np.where(lens <= 128, 0.47 * lens, np.where(lens <= 512, 0.42 * lens, 0.37 * lens)))
+        per = [cost[b[i]:b[i + 1]].sum() for i in range(world)]
+        assert max(per) <= 1.15 * (sum(per) / world) + cost.max()
+    # short rows weigh more per nonzero than heavy ones: the cost split differs from the nnz split
+    lens2 = np.concatenate([rng.integers(1, 30, 8000), rng.integers(600, 5000, 60)])
+    ptr2 = np.concatenate([[0], np.cumsum(lens2)]).astype(np.int64)
+    assert partition_by_cost(ptr2, 2) != partition_by_nnz(ptr2, 2)
+    assert partition_by_cost(np.array([0, 3, 6], np.int64), 2) == [0, 1, 2]
