@@ -104,17 +104,38 @@ __device__ __forceinline__ void pc_store(const CdSide& a, int64_t local_pos, dou
   else pc_store_at(a, a.pc_map[local_pos], v);
 }
 
-// Second phase of the staged scheme: thread k moves the k-th value in DESTINATION order
-// (route_dst ascending, so neighbouring threads write neighbouring addresses of the same peer).
-__global__ void pc_route_kernel(const double* __restrict__ stage, const uint32_t* __restrict__ route_src,
-                                const uint32_t* __restrict__ route_dst, int64_t n, PcOut out) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t g = route_dst[k];
+// Second phase of the staged scheme: the k-th value in DESTINATION order goes to its owner (route_dst
+// ascending, so neighbouring threads write neighbouring addresses of the same peer).  A small persistent grid
+// (grid-stride, four independent gathers in flight per thread): it runs on a side stream UNDER the Gram kernel
+// of the same half-epoch, and a grid of a million short blocks would simply queue in front of / behind the Gram's
+// CTAs instead of sharing the SMs with them (measured at 2 GPUs: 9.5 ms per half-epoch, not hidden).
+__device__ __forceinline__ void pc_route_one(const double* __restrict__ stage, uint32_t src, uint32_t g, const PcOut& out) {
   int r = 0;
 #pragma unroll
   for (int t = 1; t < 8; t++) r += (t < out.n && g >= out.bound[t]) ? 1 : 0;
-  out.base[r][g - out.bound[r]] = stage[route_src[k]];
+  out.base[r][g - out.bound[r]] = stage[src];
+}
+__global__ void __launch_bounds__(256)
+pc_route_kernel(const double* __restrict__ stage, const uint32_t* __restrict__ route_src,
+                const uint32_t* __restrict__ route_dst, int64_t n, PcOut out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; k + 3 * stride < n; k += 4 * stride) {
+    uint32_t s[4], g[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { s[u] = route_src[k + u * stride]; g[u] = route_dst[k + u * stride]; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = stage[s[u]];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int r = 0;
+#pragma unroll
+      for (int t = 1; t < 8; t++) r += (t < out.n && g[u] >= out.bound[t]) ? 1 : 0;
+      out.base[r][g[u] - out.bound[r]] = v[u];
+    }
+  }
+  for (; k < n; k += stride) pc_route_one(stage, route_src[k], route_dst[k], out);
   if (out.n > 1) __threadfence_system();   // see peers_release
 }
 

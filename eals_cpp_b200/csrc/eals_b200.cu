@@ -229,6 +229,7 @@ struct eals_model {
   cudaStream_t side_stream = nullptr;   // routing of the final predictions runs here, under the Gram
   cudaEvent_t ev_swept = nullptr, ev_routed = nullptr;
   bool route_pending = false;
+  int route_todo = 0;            // 1 / 2: the user / item sweep's staged predictions still have to be routed
   bool local_peers = false;      // peers are plain pointers of models in this process (eals_group), not CUDA IPC mappings
   bool pc_attached = false;      // caches usable: single rank, or both peers' cache sets mapped
   bool pc_users_attached = false, pc_items_attached = false;
@@ -1023,9 +1024,35 @@ int launch_cd(eals_model* m, Side& s, const CdSide& a, int only_row) {
   return EALS_OK;
 }
 
-// The routing copy of the previous sweep (side stream) must be complete before anything that follows on the
-// model's stream is allowed to mean "this half-epoch is done".
+// Launch the routing copy the last sweep left behind: on the side stream (after the sweep's kernels), or on the
+// model's own stream.
+int launch_route(eals_model* m, bool on_side_stream) {
+  if (!m->route_todo) return EALS_OK;
+  const bool user = m->route_todo == 1;
+  m->route_todo = 0;
+  static const bool inline_route = getenv("EALS_ROUTE_INLINE") && getenv("EALS_ROUTE_INLINE")[0] == '1';
+  const Side& s = user ? m->users : m->items;
+  const eals::PcOut& out = user ? m->out_to_items : m->out_to_users;
+  cudaStream_t rs = m->stream;
+  if (on_side_stream && !inline_route) {
+    CU(cudaStreamWaitEvent(m->side_stream, m->ev_swept, 0));
+    rs = m->side_stream;
+  }
+  const int grid = (int)std::min<int64_t>((s.nnz + 255) / 256, 2 * m->sm_count);
+  eals::pc_route_kernel<<<grid, 256, 0, rs>>>(user ? m->pc_stage_u : m->pc_stage_i, user ? m->route_src_u : m->route_src_i,
+                                              user ? m->route_dst_u : m->route_dst_i, s.nnz, out);
+  OK(check_launch(m));
+  if (rs != m->stream) {
+    CU(cudaEventRecord(m->ev_routed, m->side_stream));
+    m->route_pending = true;
+  }
+  return EALS_OK;
+}
+
+// The routing copy of the previous sweep must be complete (in stream order) before anything that follows on
+// the model's stream is allowed to mean "this half-epoch is done".
 int join_route(eals_model* m) {
+  OK(launch_route(m, false));
   if (m->route_pending) {
     CU(cudaStreamWaitEvent(m->stream, m->ev_routed, 0));
     m->route_pending = false;
@@ -1068,28 +1095,17 @@ int sweep(eals_model* m, bool user, int only_row) {
   else      { DISPATCH_LD(m->LD, OK((launch_cd<LD, false>(m, s, a, only_row)))); }
   if (a.pc_stage && s.nnz > 0) {
     // Second phase: staged predictions to their owners, in destination order.  Nobody needs them before the
-    // NEXT half-epoch's sweep, so the copy runs on a side stream under this half-epoch's Gram kernel and is
-    // joined at the end of gram() — i.e. before the all-reduce that orders the ranks (round 1 had it on the
-    // sweep's stream: 7 % of the step at 2 GPUs).
-    static const bool inline_route = getenv("EALS_ROUTE_INLINE") && getenv("EALS_ROUTE_INLINE")[0] == '1';
-    cudaStream_t rs = m->stream;
-    if (!inline_route) {
-      if (!m->side_stream) {
-        CU(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&m->ev_swept, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&m->ev_routed, cudaEventDisableTiming));
-      }
-      CU(cudaEventRecord(m->ev_swept, m->stream));
-      CU(cudaStreamWaitEvent(m->side_stream, m->ev_swept, 0));
-      rs = m->side_stream;
+    // NEXT half-epoch's sweep, so the copy is launched by gram() on a side stream right behind the Gram's main
+    // kernel (a small persistent grid that shares the SMs with it) and joined before gram() returns — i.e.
+    // before the all-reduce that orders the ranks.  Round 1 had it on the sweep's stream: 7 % of the step at
+    // 2 GPUs.  A caller that never calls gram() gets it inline at the next sweep / sync (join_route).
+    if (!m->side_stream) {
+      CU(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&m->ev_swept, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&m->ev_routed, cudaEventDisableTiming));
     }
-    eals::pc_route_kernel<<<(unsigned)((s.nnz + 255) / 256), 256, 0, rs>>>(
-        a.pc_stage, user ? m->route_src_u : m->route_src_i, user ? m->route_dst_u : m->route_dst_i, s.nnz, a.pc_out);
-    OK(check_launch(m));
-    if (!inline_route) {
-      CU(cudaEventRecord(m->ev_routed, m->side_stream));
-      m->route_pending = true;
-    }
+    CU(cudaEventRecord(m->ev_swept, m->stream));
+    m->route_todo = user ? 1 : 2;
   }
   return sync_if_debug(m);
 }
@@ -1099,9 +1115,14 @@ int launch_gram(eals_model* m, const double* X, const double* w, int r0, int r1,
   using C = eals::GramCfg<LD>;
   int nslabs = std::max(1, std::min(2 * m->sm_count, (r1 - r0 + 127) / 128));
   OK(ensure_partials(m, (size_t)C::NPAIR * nslabs * C::TB * C::TB));
-  dim3 grid(nslabs, C::NPAIR);
-  eals::gram_partial_kernel<LD><<<grid, eals::kGramThreads, 0, m->stream>>>(X, w, r0, r1, m->partials);
+  // diagonal block pairs (all of them for K <= 128): lower-triangular tiles only; LD = 256 adds the full (1, 0) block
+  eals::gram_partial_kernel<LD, true><<<dim3(nslabs, C::NB), eals::kGramThreads, 0, m->stream>>>(X, w, r0, r1, m->partials, 0, 2);
   OK(check_launch(m));
+  if (C::NB == 2) {
+    eals::gram_partial_kernel<LD, false><<<dim3(nslabs, 1), eals::kGramThreads, 0, m->stream>>>(X, w, r0, r1, m->partials, 1, 1);
+    OK(check_launch(m));
+  }
+  OK(launch_route(m, true));     // the pending prediction-cache routing shares the SMs with the kernel above
   const int total = C::NPAIR * C::TB * C::TB;
   eals::gram_reduce_kernel<LD><<<(total + 255) / 256, 256, 0, m->stream>>>(m->partials, nslabs, m->K, S);
   return check_launch(m);

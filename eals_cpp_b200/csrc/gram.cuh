@@ -27,33 +27,52 @@ struct GramCfg {
 
 // partials layout: [pair][slab][TB*TB]
 //
-// Tensor-core version (fp64 mma.sync.m8n8k4): the CTA's 8 warps tile the TB x TB output block as
-// 8 x 8 DMMA tiles (warp w owns tile rows [w*TB/8 ...) — for TB = 128 two tile rows, i.e. 2 x 16 tiles
-// would be 64 accumulator registers; instead each warp owns a (TB/8) x ... strip, see below); rows of X
-// are staged 16 at a time through shared memory (A = X^T chunk, B = diag(w) X chunk).
-template <int LD>
+// Tensor-core version (fp64 mma.sync.m8n8k4): the CTA's 8 warps share the 8 x 8 DMMA tiles of the TB x TB
+// output block; rows of X are staged 16 at a time through shared memory (A = X^T chunk, B = diag(w) X chunk).
+// TRI (diagonal block pairs, i.e. everything for K <= 128): S is symmetric, so only the tiles on and below
+// the tile diagonal are computed — 136 instead of 256 for TB = 128, 17 per warp — and the reduction mirrors
+// them, exactly like the reference's loop over k <= f (MF_fastALS.cpp:586-593).  Round 1 computed the full
+// block: 2x the DMMA work of a kernel that runs at the DMMA rate.
+template <int LD, bool TRI>
 __global__ void __launch_bounds__(kGramThreads)
 gram_partial_kernel(const double* __restrict__ X, const double* __restrict__ w, int r0, int r1,
-                    double* __restrict__ partials) {
+                    double* __restrict__ partials, int pair_base, int pair_step) {
   using C = GramCfg<LD>;
   constexpr int TB = C::TB;
   constexpr int NT = TB / 8;                 // 8 x 8 tiles per dimension of the output block
-  constexpr int TPW = (NT * NT + 7) / 8;     // tiles per warp (TB = 128: 32, 64: 8, 32: 2, 16: 1)
+  constexpr int NTILES = TRI ? NT * (NT + 1) / 2 : NT * NT;
+  constexpr int TPW = (NTILES + 7) / 8;      // tiles per warp (TB = 128: 17 / 32, 64: 5 / 8, 32: 2, 16: 1)
   // staged rows: As[r][c] = X[row][bi*TB + c], Bs[r][c] = w[row] * X[row][bj*TB + c]; stride TB + 4
   // doubles keeps the 4-row x 8-column fragment reads on distinct banks
   constexpr int ST = TB + 4;
   __shared__ double As[kGramChunk][ST];
   __shared__ double Bs[kGramChunk][ST];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = pair_base + blockIdx.y * pair_step;
   int bi = 0, bj = 0;
   if (C::NB == 2) {  // pair 0 -> (0,0), 1 -> (1,0), 2 -> (1,1)
-    bi = blockIdx.y >= 1;
-    bj = blockIdx.y == 2;
+    bi = pair >= 1;
+    bj = pair == 2;
   }
   const int rows = r1 - r0;
   const int per = (rows + gridDim.x - 1) / gridDim.x;
   const int s0 = r0 + blockIdx.x * per;
   const int s1 = min(s0 + per, r1);
+
+  // this warp's tiles: tile index -> (ti, tj); triangular enumeration row by row: idx = ti (ti + 1) / 2 + tj
+  int ti_[TPW], tj_[TPW];
+#pragma unroll
+  for (int t = 0; t < TPW; t++) {
+    const int tile = warp * TPW + t;
+    int ti = 0, tj = 0;
+    if (TRI) {
+      while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+      tj = tile - ti * (ti + 1) / 2;
+    } else {
+      ti = tile / NT; tj = tile % NT;
+    }
+    ti_[t] = ti; tj_[t] = tj;
+  }
 
   double acc[TPW][2];
 #pragma unroll
@@ -77,11 +96,9 @@ gram_partial_kernel(const double* __restrict__ X, const double* __restrict__ w, 
     for (int k0 = 0; k0 < kGramChunk; k0 += 4) {
 #pragma unroll
       for (int t = 0; t < TPW; t++) {
-        const int tile = warp * TPW + t;
-        if (tile < NT * NT) {
-          const int ti = tile / NT, tj = tile % NT;
-          const double a = As[k0 + (lane & 3)][ti * 8 + (lane >> 2)];   // A[row = f][col = k]
-          const double b = Bs[k0 + (lane & 3)][tj * 8 + (lane >> 2)];   // B[row = k][col = f']
+        if (warp * TPW + t < NTILES) {
+          const double a = As[k0 + (lane & 3)][ti_[t] * 8 + (lane >> 2)];   // A[row = f][col = k]
+          const double b = Bs[k0 + (lane & 3)][tj_[t] * 8 + (lane >> 2)];   // B[row = k][col = f']
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                        : "+d"(acc[t][0]), "+d"(acc[t][1])
                        : "d"(a), "d"(b));
@@ -90,20 +107,20 @@ gram_partial_kernel(const double* __restrict__ X, const double* __restrict__ w, 
     }
     __syncthreads();
   }
-  double* out = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TB * TB;
+  double* out = partials + ((size_t)pair * gridDim.x + blockIdx.x) * TB * TB;
 #pragma unroll
   for (int t = 0; t < TPW; t++) {
-    const int tile = warp * TPW + t;
-    if (tile < NT * NT) {
-      const int ti = tile / NT, tj = tile % NT;
-      const int rr = ti * 8 + (lane >> 2), cc = tj * 8 + 2 * (lane & 3);
+    if (warp * TPW + t < NTILES) {
+      const int rr = ti_[t] * 8 + (lane >> 2), cc = tj_[t] * 8 + 2 * (lane & 3);
       out[rr * TB + cc] = acc[t][0];
       out[rr * TB + cc + 1] = acc[t][1];
     }
   }
 }
 
-// S[f][k] = sum over slabs (ascending) of the partials; rows f >= K are not written.
+// S[f][k] = sum over slabs (ascending) of the partials; rows f >= K are not written.  Diagonal block pairs
+// hold the lower triangle only (elements with column <= row): those are summed and mirrored, so S comes out
+// exactly symmetric, as the reference's does.
 template <int LD>
 __global__ void gram_reduce_kernel(const double* __restrict__ partials, int nslabs, int K,
                                    double* __restrict__ S) {
@@ -117,12 +134,13 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partials, int nsla
     bi = pair >= 1;
     bj = pair == 2;
   }
+  if (bi == bj && j > i) return;             // upper triangle of a diagonal block: written by its mirror image
   const double* p = partials + (size_t)pair * nslabs * C::TB * C::TB + e;
   double s = 0.0;
   for (int sl = 0; sl < nslabs; sl++) s += p[(size_t)sl * C::TB * C::TB];
   const int f = bi * C::TB + i, k = bj * C::TB + j;
   if (f < K) S[(size_t)f * LD + k] = s;
-  if (bi != bj && k < K) S[(size_t)k * LD + f] = s;
+  if (f != k && k < K) S[(size_t)k * LD + f] = s;
 }
 
 // Rank-1 patch used by the single-row API (update_user_SU / update_item_SV,

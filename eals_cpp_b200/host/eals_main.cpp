@@ -16,6 +16,8 @@
 // --gpus N: shard users and items over GPUs device .. device+N-1 (eals_group: the exchange runs inside the
 // library); --devices lists them explicitly — a repeated id puts several ranks on one GPU.
 // --save / --load: factor checkpoint after training / instead of the random initialisation.
+// --dump-split FILE: write the hold-one-out split (per user: test item, then the train items) and stop before
+// the model is built — needs no GPU; the loader is checked against the reference's own binary this way.
 // --online U,I: after training and evaluation, add the interaction (U, I) with the online update
 // (updateModel, MF_fastALS.cpp:223-242) and print the prediction before and after.
 #include <algorithm>
@@ -45,7 +47,7 @@ int main(int argc, char** argv) {
   bool showProgress = false, showLoss = true, exact = false;
   int online_u = -1, online_i = -1, n_gpus = 1;
   std::vector<int> devices;
-  std::string save_path, load_path;
+  std::string save_path, load_path, dump_split;
   for (int a = 1; a < argc; a++) {
     auto is = [&](const char* f) { return std::strcmp(argv[a], f) == 0; };
     auto next = [&]() -> const char* { if (a + 1 >= argc) { std::fprintf(stderr, "missing value after %s\n", argv[a]); std::exit(2); } return argv[++a]; };
@@ -61,6 +63,7 @@ int main(int argc, char** argv) {
     else if (is("--devices")) { std::istringstream in(next()); for (std::string t; std::getline(in, t, ',');) devices.push_back(std::atoi(t.c_str())); }
     else if (is("--save")) save_path = next();
     else if (is("--load")) load_path = next();
+    else if (is("--dump-split")) dump_split = next();
     else if (is("--no-loss")) showLoss = false;
     else if (is("--exact-eval")) exact = true;
     else if (is("--online")) { if (std::sscanf(next(), "%d,%d", &online_u, &online_i) != 2) { std::fprintf(stderr, "--online wants U,I\n"); return 2; } }
@@ -112,6 +115,16 @@ int main(int argc, char** argv) {
   std::cout << "#Ratings\t" << trainMatrix.itemCount() << "\t" << "tests\t" << testRatings.size() << std::endl;
   std::cout << "==========================================" << std::endl;
   if ((int)testRatings.size() != userCount) { std::fprintf(stderr, "every user needs at least one rating\n"); return EXIT_FAILURE; }
+  if (!dump_split.empty()) {
+    std::ofstream out(dump_split);
+    out << userCount << " " << itemCount << "\n";
+    for (int u = 0; u < userCount; u++) {
+      out << testRatings[u].itemId;
+      for (const auto& kv : by_user[u]) out << " " << kv.first;
+      out << "\n";
+    }
+    return out.good() ? 0 : EXIT_FAILURE;
+  }
 
   try {
     if (!devices.empty()) n_gpus = (int)devices.size();

@@ -91,3 +91,29 @@ def test_cpp_driver_trains_evaluates_and_updates_online(tmp_path, devices):
     assert abs(got_before - before) < 1e-10
     assert abs(got_after - float(port.U[u] @ port.V[i])) < 1e-10
     assert abs(got_loss - port.loss()) <= 1e-10 * abs(port.loss())
+
+
+def test_cpp_driver_transcript_equals_the_reference_binary(tmp_path):
+    """Same ratings file (tied timestamps, duplicates), the reference's OWN driver (oracle/_ref/eals_ref_main =
+    main.cpp + the five TUs, unmodified, travels to the GPU box prebuilt) against ours with the run.sh defaults
+    (K=64, 20 iterations, top-10): every printed loss and the final <hr, ndcg, prec> line agree to the 6
+    significant digits the reference prints."""
+    from test_oracle import _ratings_with_ties, _reference_transcript
+    from eals_cpp_b200 import build
+    _ratings_with_ties(str(tmp_path / "yelp.rating"))
+    losses, metrics, counts, ref_out = _reference_transcript(tmp_path)
+    exe = build.build_host_example()
+    res = subprocess.run([exe, "--data", str(tmp_path / "yelp.rating")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    out = res.stdout
+    for key in ("#Users", "#items", "#Ratings"):
+        assert f"{key}\t{counts[key]}" in out
+    ours = [float(x) for x in re.findall(r"Iter=\d+ \S+ [-+] loss:(\S+)", out)]
+    assert len(ours) == 20
+    assert ours == pytest.approx(losses, rel=2e-6)
+    got = [float(x) for x in re.search(r"<hr, ndcg, prec>: \t(\S+)\t(\S+)\t(\S+)", out).groups()]
+    assert got == pytest.approx(metrics, rel=2e-6, abs=1e-9)
+    # the same lines in the same order (timings aside): a transcript diff is empty up to the numbers' noise
+    strip = lambda t: [re.sub(r"[-+]?\d+(\.\d+)?(e[-+]?\d+)?", "#", l) for l in t.strip().split("\n") if l.strip()]
+    ref_lines = [l for l in strip(ref_out) if not l.startswith("double free")]
+    assert strip(out)[:len(ref_lines)] == ref_lines

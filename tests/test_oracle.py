@@ -10,6 +10,8 @@ The restatement follows the reference's operation order and is compiled with -ff
 agreement is BIT-EXACT except through libm `pow` in the item weights (same libm here: also exact).
 """
 import os
+import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -153,3 +155,61 @@ def test_parallel_init_stream_is_the_sequential_stream(monkeypatch):
     out = np.empty(100_003)
     lib.eals_debug_init_stream(C.c_double(1.5), C.c_double(2.0), out.ctypes.data_as(C.c_void_p), C.c_int64(len(out)))
     assert np.array_equal(out, port.normal_fill(len(out), 1.5, 2.0))
+
+
+def _ratings_with_ties(path, M=90, N=60, seed=8):
+    """`user item score timestamp` lines with MANY tied timestamps (also for the newest rating of a user) and
+    duplicate (u, i) pairs: which of the tied ratings becomes the test item is decided by libstdc++'s unstable
+    std::sort (main.cpp:122-124) and is part of the reference's behaviour."""
+    rng = np.random.default_rng(seed)
+    with open(path, "w") as f:
+        for u in range(M):
+            n = int(rng.integers(4, 40))
+            items = rng.integers(0, N, size=n)
+            ts = rng.integers(1, 6, size=n)              # only 5 distinct timestamps
+            for it, t in zip(items, ts):
+                f.write(f"{u}\t{it}\t{float(rng.integers(1, 6))}\t{t}\n")
+
+
+def _reference_transcript(tmp_path):
+    """Run the reference's own driver (oracle/_ref/eals_ref_main = main.cpp unmodified) on tmp_path/yelp.rating."""
+    exe = os.path.join(os.path.dirname(bindings.REF_SO), "eals_ref_main")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/eals_ref_main not built (no /root/reference at build time)")
+    res = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    out = res.stdout                                     # exits through its double free AFTER printing (SURVEY.md §3.1)
+    losses = [float(x) for x in re.findall(r"Iter=\d+ \S+ [-+] loss:(\S+)", out)]
+    m = re.search(r"<hr, ndcg, prec>: \t(\S+)\t(\S+)\t(\S+)", out)
+    assert len(losses) == 20 and m, out[-2000:]
+    counts = {k: int(re.search(k + r"\t(\d+)", out).group(1)) for k in ("#Users", "#items", "#Ratings")}
+    return losses, [float(x) for x in m.groups()], counts, out
+
+
+def test_loader_split_matches_the_reference_binary_with_tied_timestamps(tmp_path):
+    """Our loader (host/eals_main.cpp --dump-split, no GPU) against the reference's own main.cpp on the same
+    file, ties and duplicates included: same counts, and the oracle trained on OUR split reproduces the
+    reference binary's 20 printed losses and its final metrics (which depend on every tie decision)."""
+    import subprocess as sp
+    from eals_cpp_b200 import build
+    _ratings_with_ties(str(tmp_path / "yelp.rating"))
+    losses, metrics, counts, _ = _reference_transcript(tmp_path)
+    exe = build.build_host_example()
+    split = tmp_path / "split.txt"
+    res = sp.run([exe, "--data", str(tmp_path / "yelp.rating"), "--dump-split", str(split)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    lines = open(split).read().split("\n")
+    M, N = (int(x) for x in lines[0].split())
+    rows, gt = [], []
+    for u in range(M):
+        v = [int(x) for x in lines[1 + u].split()]
+        gt.append(v[0]); rows.append(v[1:])
+    assert (M, N) == (counts["#Users"], counts["#items"]) and sum(len(r) for r in rows) == counts["#Ratings"]
+    assert f"#Ratings\t{counts['#Ratings']}" in res.stdout
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col_idx = np.concatenate([np.array(r, np.int32) for r in rows])
+    port = PortModel(M, N, row_ptr, col_idx, factors=64)               # main.cpp:133-144 defaults
+    for it in range(20):
+        port.update_user(); port.update_item()
+        assert abs(port.loss() - losses[it]) <= 2e-6 * abs(losses[it]), it   # printed with 6 significant digits
+    want = port.evaluate(np.array(gt, np.int32), 10, compat=True)[0]
+    assert np.allclose(want, metrics, rtol=2e-6, atol=1e-9)

@@ -38,6 +38,9 @@ def main():
     out["metrics"] = res.tolist()
     out.update(fals.eval_stats())
     out["survivors"] = int((cnt <= topK).sum())
+    if os.environ.get("EVAL_PROBE_NO_SAMPLE") == "1":
+        print(json.dumps(out), flush=True)
+        return
     rng = np.random.default_rng(0)
     surv = np.flatnonzero(cnt <= topK)
     sample = np.concatenate([rng.choice(M, 30, replace=False), rng.choice(surv, min(30, len(surv)), replace=False)]) if len(surv) else rng.choice(M, 30, replace=False)
