@@ -103,7 +103,7 @@ def test_cpp_driver_transcript_equals_the_reference_binary(tmp_path):
     _ratings_with_ties(str(tmp_path / "yelp.rating"))
     losses, metrics, counts, ref_out = _reference_transcript(tmp_path)
     exe = build.build_host_example()
-    res = subprocess.run([exe, "--data", str(tmp_path / "yelp.rating")], capture_output=True, text=True, timeout=600)
+    res = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)   # default --data yelp.rating
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = res.stdout
     for key in ("#Users", "#items", "#Ratings"):
