@@ -272,7 +272,7 @@ cd_warp_block_kernel(CdSide a, const int32_t* __restrict__ order, int first, int
         if (j < n_n) {
           id_n[m] = a.idx[p0_n + j];
           if (a.use_cache) pc_n[m] = a.pc_in[p0_n + j];
-          if (a.pc_out.n && !a.pc_stage) g_n[m] = a.pc_map[p0_n + j];
+          if (a.pc_out.n) g_n[m] = a.pc_map[p0_n + j];
         }
       }
     } else if (USER) {

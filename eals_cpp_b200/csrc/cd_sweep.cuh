@@ -61,9 +61,11 @@ struct CdSide {
   const double* pc_in;     // nullptr: no cache
   const uint32_t* pc_map;  // per local nonzero: its global position in the other orientation
   PcOut pc_out;
-  // Multi-rank: final predictions are first written here in THIS side's nonzero order (coalesced) and
-  // routed to their owners afterwards by pc_route_kernel in destination order — scattered 8-byte
-  // stores straight into peer memory were far slower than the gather they replace (r01f).
+  // Multi-rank: final predictions are first written to a LOCAL staging array, already in destination order
+  // (pc_map then holds, per local nonzero, its slot in that order), and copied to their owners afterwards by
+  // pc_route_kernel — a pure streaming copy.  Scattered 8-byte stores straight into peer memory were far
+  // slower than the gather they replace (r01f); staging in source order and gathering in the copy kernel cost
+  // 5 ms per half-epoch at 2 GPUs (r02i).
   double* pc_stage;        // nullptr: store directly through pc_map / pc_out
   int use_cache;           // 1: pc_in is valid on entry, read it instead of recomputing
   PeerSet peers;        // other ranks' replicas of X (n = 0: none)
@@ -95,48 +97,35 @@ __device__ __forceinline__ void pc_store_at(const CdSide& a, uint32_t g, double 
 // The final prediction of local nonzero local_pos (its position g in the other orientation already
 // looked up, or not needed when the values are staged).
 __device__ __forceinline__ void pc_emit(const CdSide& a, int64_t local_pos, uint32_t g, double v) {
-  if (a.pc_stage) a.pc_stage[local_pos] = v;
-  else pc_store_at(a, g, v);
+  (void)local_pos;
+  if (a.pc_stage) a.pc_stage[g] = v;      // g = slot in destination order
+  else pc_store_at(a, g, v);              // g = global position in the other orientation
 }
 
 __device__ __forceinline__ void pc_store(const CdSide& a, int64_t local_pos, double v) {
-  if (a.pc_stage) a.pc_stage[local_pos] = v;
-  else pc_store_at(a, a.pc_map[local_pos], v);
+  pc_emit(a, local_pos, a.pc_map[local_pos], v);
 }
 
-// Second phase of the staged scheme: the k-th value in DESTINATION order goes to its owner (route_dst
-// ascending, so neighbouring threads write neighbouring addresses of the same peer).  A small persistent grid
-// (grid-stride, four independent gathers in flight per thread): it runs on a side stream UNDER the Gram kernel
-// of the same half-epoch, and a grid of a million short blocks would simply queue in front of / behind the Gram's
-// CTAs instead of sharing the SMs with them (measured at 2 GPUs: 9.5 ms per half-epoch, not hidden).
-__device__ __forceinline__ void pc_route_one(const double* __restrict__ stage, uint32_t src, uint32_t g, const PcOut& out) {
-  int r = 0;
-#pragma unroll
-  for (int t = 1; t < 8; t++) r += (t < out.n && g >= out.bound[t]) ? 1 : 0;
-  out.base[r][g - out.bound[r]] = stage[src];
-}
+// Second phase of the staged scheme: slot k of the staging array (DESTINATION order: route_dst ascending, so
+// neighbouring threads read neighbouring values and write neighbouring addresses of the same peer) goes to its
+// owner.  A small persistent grid, launched on a side stream right behind the Gram's main kernel.
 __global__ void __launch_bounds__(256)
-pc_route_kernel(const double* __restrict__ stage, const uint32_t* __restrict__ route_src,
-                const uint32_t* __restrict__ route_dst, int64_t n, PcOut out) {
+pc_route_kernel(const double* __restrict__ stage, const uint32_t* __restrict__ route_dst, int64_t n, PcOut out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; k + 3 * stride < n; k += 4 * stride) {
-    uint32_t s[4], g[4];
-    double v[4];
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const uint32_t g = route_dst[k];
+    int r = 0;
 #pragma unroll
-    for (int u = 0; u < 4; u++) { s[u] = route_src[k + u * stride]; g[u] = route_dst[k + u * stride]; }
-#pragma unroll
-    for (int u = 0; u < 4; u++) v[u] = stage[s[u]];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      int r = 0;
-#pragma unroll
-      for (int t = 1; t < 8; t++) r += (t < out.n && g[u] >= out.bound[t]) ? 1 : 0;
-      out.base[r][g[u] - out.bound[r]] = v[u];
-    }
+    for (int t = 1; t < 8; t++) r += (t < out.n && g >= out.bound[t]) ? 1 : 0;
+    out.base[r][g - out.bound[r]] = stage[k];
   }
-  for (; k < n; k += stride) pc_route_one(stage, route_src[k], route_dst[k], out);
   if (out.n > 1) __threadfence_system();   // see peers_release
+}
+
+// inv[perm[k]] = k
+__global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, int64_t n, uint32_t* __restrict__ inv) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) inv[perm[k]] = (uint32_t)k;
 }
 
 }  // namespace eals

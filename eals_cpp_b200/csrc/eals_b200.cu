@@ -347,8 +347,9 @@ __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
   if (t < n) v[t] = (uint32_t)t;
 }
 
-// Destination order of one side's nonzeros: route_dst = the map values ascending, route_src = the local
-// positions they belong to (cub radix sort, once per matrix).
+// Destination order of one side's nonzeros (cub radix sort, once per matrix): route_dst = the map values
+// ascending; rsrc ends up holding, per LOCAL nonzero, its slot in that order — the index the sweep kernels
+// scatter their final predictions through (CdSide::pc_map in staged mode).
 int build_routes(eals_model* m, const uint32_t* map, int64_t n, double** stage, size_t* cap_stage,
                  uint32_t** rsrc, size_t* cap_rsrc, uint32_t** rdst, size_t* cap_rdst) {
   OK(dev_reserve(stage, cap_stage, (size_t)n));
@@ -363,8 +364,13 @@ int build_routes(eals_model* m, const uint32_t* map, int64_t n, double** stage, 
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, map, *rdst, iota, *rsrc, (int)n, 0, 32, m->stream);
   OK(dev_reserve(&m->route_tmp, &m->cap_route_tmp, std::max<size_t>(tmp_bytes, 16)));
   const cudaError_t e = cub::DeviceRadixSort::SortPairs(m->route_tmp, tmp_bytes, map, *rdst, iota, *rsrc, (int)n, 0, 32, m->stream);
-  cudaStreamSynchronize(m->stream);
   if (e != cudaSuccess) return fail(EALS_ERR_CUDA, "route sort -> %s", cudaGetErrorString(e));
+  // the kernels scatter into the staging array through the INVERSE permutation (local nonzero -> slot in
+  // destination order); rsrc is replaced by it (the staging buffer, not live yet, is the scratch)
+  eals::invert_perm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(*rsrc, n, iota);
+  OK(check_launch(m));
+  CU(cudaMemcpyAsync(*rsrc, iota, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
   return EALS_OK;
 }
 
@@ -1038,9 +1044,8 @@ int launch_route(eals_model* m, bool on_side_stream) {
     CU(cudaStreamWaitEvent(m->side_stream, m->ev_swept, 0));
     rs = m->side_stream;
   }
-  const int grid = (int)std::min<int64_t>((s.nnz + 255) / 256, 2 * m->sm_count);
-  eals::pc_route_kernel<<<grid, 256, 0, rs>>>(user ? m->pc_stage_u : m->pc_stage_i, user ? m->route_src_u : m->route_src_i,
-                                              user ? m->route_dst_u : m->route_dst_i, s.nnz, out);
+  const int grid = (int)std::min<int64_t>((s.nnz + 255) / 256, 4 * m->sm_count);
+  eals::pc_route_kernel<<<grid, 256, 0, rs>>>(user ? m->pc_stage_u : m->pc_stage_i, user ? m->route_dst_u : m->route_dst_i, s.nnz, out);
   OK(check_launch(m));
   if (rs != m->stream) {
     CU(cudaEventRecord(m->ev_routed, m->side_stream));
@@ -1085,7 +1090,10 @@ int sweep(eals_model* m, bool user, int only_row) {
     a.pc_in = user ? m->pc_u : m->pc_i;
     a.pc_map = user ? m->map_u : m->map_i;
     a.pc_out = user ? m->out_to_items : m->out_to_users;
-    if (m->routed) a.pc_stage = user ? m->pc_stage_u : m->pc_stage_i;
+    if (m->routed) {     // staged: the map is the slot in destination order (build_routes)
+      a.pc_stage = user ? m->pc_stage_u : m->pc_stage_i;
+      a.pc_map = user ? m->route_src_u : m->route_src_i;
+    }
     a.use_cache = in_valid ? 1 : 0;
     m->sweeps_since_fresh = in_valid ? m->sweeps_since_fresh + 1 : 0;
     in_valid = false;    // this side's cache describes the factors BEFORE this sweep
