@@ -1718,7 +1718,7 @@ int scan_tc(eals_model* m, int n, const int32_t* d_users, const double* d_gts, i
     }
     tm.lap("eval: candidate emission (MODE 1)");
     if (got) {
-      tc::eval_rescore_kernel<<<8 * m->sm_count, 256, 0, st>>>(m->U, m->V, K, LD, d_users, 0, d_gts, ws.pairs.p, d_np, got, ws.cnt_exact.p);
+      tc::eval_rescore_kernel<<<16 * m->sm_count, 128, 0, st>>>(m->U, m->V, K, LD, d_users, 0, d_gts, ws.pairs.p, d_np, got, ws.cnt_exact.p);
       OK(check_launch(m));
     }
   }
@@ -2241,7 +2241,7 @@ int eals_predict(eals_model* m, int32_t u, int32_t i, double* score) {
   OK(ensure_partials(m, 16));
   int32_t* d_gt = reinterpret_cast<int32_t*>(m->partials + 8);
   CU(cudaMemcpyAsync(d_gt, &i, sizeof(int32_t), cudaMemcpyHostToDevice, m->stream));
-  eals::eval_gt_score_kernel<<<1, 32, 0, m->stream>>>(m->U, m->V, d_gt, nullptr, u, 1, m->K, m->LD, m->partials);
+  eals::eval_gt_score_kernel<<<1, 128, 0, m->stream>>>(m->U, m->V, d_gt, nullptr, u, 1, m->K, m->LD, m->partials);
   OK(check_launch(m));
   CU(cudaMemcpyAsync(score, m->partials, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));

@@ -43,6 +43,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "eval.cuh"
 
 namespace eals {
 namespace tc {
@@ -568,20 +569,30 @@ __global__ void gather_rows_kernel(const __half* __restrict__ H, int KP, const i
 // ---- exact pass over the candidates -----------------------------------------------------------------
 // One thread per pair: the reference's own score (sequential k, separately rounded products — predict(),
 // MF_fastALS.cpp:208-221), compared with the exact gt score; (int)score kept for the ranking replay.
-__global__ void eval_rescore_kernel(const double* __restrict__ U, const double* __restrict__ V, int K, int LD,
-                                    const int32_t* __restrict__ users, int u_begin, const double* __restrict__ gt_score,
-                                    EvalPair* __restrict__ pairs, const unsigned long long* __restrict__ n_pairs, unsigned long long cap,
-                                    int32_t* __restrict__ cnt_exact) {
+__global__ void __launch_bounds__(128)
+eval_rescore_kernel(const double* __restrict__ U, const double* __restrict__ V, int K, int LD,
+                    const int32_t* __restrict__ users, int u_begin, const double* __restrict__ gt_score,
+                    EvalPair* __restrict__ pairs, const unsigned long long* __restrict__ n_pairs, unsigned long long cap,
+                    int32_t* __restrict__ cnt_exact) {
+  __shared__ double sm[4][2 * 32 * 17];
   const unsigned long long n = min(*n_pairs, cap);
-  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
-    EvalPair pr = pairs[t];
-    const int u = users ? users[pr.slot] : u_begin + pr.slot;
-    const double* a = U + (size_t)u * LD;
-    const double* b = V + (size_t)pr.item * LD;
-    double acc = 0.0;
-    for (int k = 0; k < K; k++) acc = __dadd_rn(acc, __dmul_rn(a[k], b[k]));
-    if ((pr.flags & 1) && acc > gt_score[pr.slot]) atomicAdd(cnt_exact + pr.slot, 1);
-    pairs[t].key = __double2int_rz(acc);
+  // whole warps stay in the loop together (seq_dot_warp32 is warp-cooperative)
+  const unsigned long long n_round = (n + 31ull) & ~31ull;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += (unsigned long long)gridDim.x * blockDim.x) {
+    const bool live = t < n;
+    EvalPair pr{0, 0, 0, 0};
+    const double *a = nullptr, *b = nullptr;
+    if (live) {
+      pr = pairs[t];
+      const int u = users ? users[pr.slot] : u_begin + pr.slot;
+      a = U + (size_t)u * LD;
+      b = V + (size_t)pr.item * LD;
+    }
+    const double acc = eals::seq_dot_warp32(a, b, K, sm[threadIdx.x >> 5]);
+    if (live) {
+      if ((pr.flags & 1) && acc > gt_score[pr.slot]) atomicAdd(cnt_exact + pr.slot, 1);
+      pairs[t].key = __double2int_rz(acc);
+    }
   }
 }
 
