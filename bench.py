@@ -396,6 +396,13 @@ def main():
     detail_ms = fals.timings_detail()
     phase_ms, phase_calls = fals.timings_total(reset=True)
     value = 2.0 * nnz * K / (ms_step * 1e-3)
+    per_rank = None
+    if world > 1:       # every rank's own phase timers: load balance of the partition
+        mine = torch.tensor([phase_ms[k] / args.steps for k in ("user_sweep", "user_gram", "item_sweep", "item_gram")],
+                            device=f"cuda:{local_rank}", dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {k: [round(float(a[i]), 3) for a in allr] for i, k in enumerate(("user_sweep", "user_gram", "item_sweep", "item_gram"))}
 
     # roofline of the dominant kernel family: the CD sweeps (this rank's owned rows)
     peaks, peak_src = measured_peaks()
@@ -500,6 +507,12 @@ def main():
                 "engine": st["engine"], "candidate_users_this_rank": st["candidates"], "pairs_rescored_fp64_this_rank": st["pairs_rescored"],
                 "candidate_fraction_this_rank": st["candidates"] / max(1, fals.user_bounds[rank + 1] - fals.user_bounds[rank]),
                 "dense_equivalent_tflops": flop / ev[-1] / 1e12,
+                "roofline": None if "first_block" not in st else {
+                    "bound": "tensor", "kernel": "eval_filter_kernel (tcgen05.mma fp16 -> fp32 in TMEM), first item block of this rank: "
+                                                 f"{st['first_block']['users']} users x {st['first_block']['items']} items",
+                    "achieved": st["first_block"]["tflops"], "unit": "TFLOP/s", "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                    "frac": st["first_block"]["tflops"] / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                    "kernel_ms": st["first_block"]["ms"], "peak_source": peak_src + " — sustained bf16 figure: the kernel runs inside a long step"},
                 "note": "tcgen05 fp16 filter with a rigorous error bound decides the clear cases (users leave the working set once "
                         "more than topK items certainly beat the held-out one); every close call is re-scored in fp64; "
                         "dense_equivalent_tflops counts 2*M*N*K although decided users skip the rest of the catalogue"}
@@ -571,6 +584,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "phase_ms_per_step": {k: v / args.steps for k, v in phase_ms.items() if phase_calls[k]},
             "sweep_detail_ms_per_step": {k: v / args.steps for k, v in detail_ms.items()},
+            "per_rank_phase_ms_per_step": per_rank,
             "loss_after": loss, "replicas_consistent": replicas_ok,
             "configs": configs,
         }

@@ -344,20 +344,28 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
               for (int i = 0; i < kCols; i++) cnt[j] += (i < nvalid && v[i] > thr_hi) ? 1 : 0;
             }
           } else {
-            // candidate masks: bit i of m1 = "may exceed the gt score", of m2 = "|score| may reach 1"
-            uint32_t m1[2], m2[2];
+            // candidate masks: bit i of m1 = "may exceed the gt score", of m2 = "|score| may reach 1".  Almost every
+            // lane has no candidate in a given tile (0.04 per lane and tile at 10M x 2M), so a two-compare screen
+            // per score comes first and the masks are only built by the lanes that need them.
+            uint32_t m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
+            const float t_pos = fminf(thr_lo, thr_one), t_neg = -thr_one;
+            bool hit = false;
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-              uint32_t b1 = 0, b2 = 0;
+            for (int i = 0; i < kCols; i++) hit |= (v[i] >= t_pos) | (v[i] <= t_neg);
+            if (hit && slot[j] >= 0) {
 #pragma unroll
-              for (int i = 0; i < 32; i++) {
-                b1 |= (v[c * 32 + i] >= thr_lo ? 1u : 0u) << i;
-                b2 |= (fabsf(v[c * 32 + i]) >= thr_one ? 1u : 0u) << i;
+              for (int c = 0; c < 2; c++) {
+                uint32_t b1 = 0, b2 = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                  b1 |= (v[c * 32 + i] >= thr_lo ? 1u : 0u) << i;
+                  b2 |= (fabsf(v[c * 32 + i]) >= thr_one ? 1u : 0u) << i;
+                }
+                const int lim = nvalid - c * 32;
+                const uint32_t live = lim <= 0 ? 0u : (lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u));
+                m1[c] = b1 & live;
+                m2[c] = b2 & live;
               }
-              const int lim = nvalid - c * 32;
-              const uint32_t live = slot[j] < 0 || lim <= 0 ? 0u : (lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u));
-              m1[c] = b1 & live;
-              m2[c] = b2 & live;
             }
             // Warp-aggregated append into this warp's shared-memory staging buffer; the buffer goes to the global
             // list with ONE atomic per flush (one atomic per pair — ~700 dependent atomics per thread — made this

@@ -682,9 +682,14 @@ class MF_fastALS:
     def eval_stats(self):
         """Engine of the last evaluate(): 'tcgen05' (fp16 tensor-core filter + exact fp64 re-score of the close
         calls) or 'fp64' (exact tile scan), the number of candidate users and of re-scored pairs."""
-        out = np.zeros(3, np.int64)
+        out = np.zeros(6, np.int64)
         check(self.lib.eals_eval_stats(self.h, _ptr(out)))
-        return {"engine": "tcgen05" if out[0] == 1 else "fp64", "candidates": int(out[1]), "pairs_rescored": int(out[2])}
+        st = {"engine": "tcgen05" if out[0] == 1 else "fp64", "candidates": int(out[1]), "pairs_rescored": int(out[2])}
+        if out[5] > 0:
+            kp = -(-self.factors // 64) * 64
+            st["first_block"] = {"users": int(out[3]), "items": int(out[4]), "ms": out[5] / 1e3,
+                                 "tflops": 2.0 * out[3] * out[4] * kp / (out[5] * 1e-6) / 1e12}
+        return st
 
     # ---- instrumentation -----------------------------------------------------------------------------------
     def timings(self):

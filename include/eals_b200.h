@@ -203,8 +203,10 @@ int eals_evaluate_user(eals_model* m, int32_t u, int32_t gt_item, int32_t topk, 
 /* How the last eals_evaluate ran: out[0] = 1 when the scores went through the tcgen05 fp16 filter (lists of
  * >= 128 users; every close call re-scored in fp64 with the reference's operation order, so the results are
  * identical to the all-fp64 scan), 0 for the exact fp64 tile scan; out[1] = users whose certain count stayed
- * <= topK after the filter (candidates), out[2] = (user, item) pairs re-scored exactly. */
-int eals_eval_stats(eals_model* m, int64_t out[3]);
+ * <= topK after the filter (candidates), out[2] = (user, item) pairs re-scored exactly; out[3], out[4], out[5] =
+ * users, items and device microseconds of the filter's FIRST item block (every user against the highest-norm
+ * items: the one launch of known shape, 2 * users * items * roundup(factors, 64) flop — the tensor roofline). */
+int eals_eval_stats(eals_model* m, int64_t out[6]);
 
 /* Plumbing for the host layer. */
 int eals_leading_dim(const eals_model* m);                 /* ld of U/V/SU/SV rows, in doubles   */
