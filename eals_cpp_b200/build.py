@@ -1,6 +1,11 @@
-"""In-tree build of libeals_b200.so (nvcc, sm_100a only).  Cross-compiles without a GPU."""
+"""In-tree build of libeals_b200.so (nvcc, sm_100a only).  Cross-compiles without a GPU.
+
+Staleness is decided by CONTENT, not by modification times: a digest of every source file and of the
+compiler flags is stored next to the artefact (`<artefact>.stamp`).  After a checkout, a copy to another
+box or a `touch`, the artefact is rebuilt exactly when it was built from different sources."""
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 
@@ -20,18 +25,40 @@ def _sources():
     return deps
 
 
+def _digest(paths, extra) -> str:
+    h = hashlib.sha256(repr(extra).encode())
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _fresh(artefact: str, digest: str) -> bool:
+    try:
+        with open(artefact + ".stamp") as f:
+            return os.path.exists(artefact) and f.read().strip() == digest
+    except OSError:
+        return False
+
+
+def _stamp(artefact: str, digest: str) -> None:
+    with open(artefact + ".stamp", "w") as f:
+        f.write(digest + "\n")
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/eals_b200.cu -> lib/libeals_b200.so if any source is newer than the library."""
+    """Compile csrc/eals_b200.cu -> lib/libeals_b200.so unless it was built from exactly these sources."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB):
-        t = os.path.getmtime(LIB)
-        if all(os.path.getmtime(s) <= t for s in _sources()):
-            return LIB
+    digest = _digest(_sources(), NVCC_FLAGS)
+    if not force and _fresh(LIB, digest):
+        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "eals_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
+    _stamp(LIB, digest)
     return LIB
 
 
@@ -42,11 +69,15 @@ def build_host_example(force: bool = False) -> str:
     out = os.path.join(LIB_DIR, "eals_main")
     if not os.path.exists(src):
         return ""
-    deps = [src, os.path.join(ROOT, "include", "MF_fastALS.h"), os.path.join(ROOT, "include", "eals_b200.h")]
-    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+    deps = [src, os.path.join(ROOT, "include", "MF_fastALS.h"), os.path.join(ROOT, "include", "eals_b200.h"),
+            os.path.join(ROOT, "include", "eals_host_types.h")]
+    cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", out,
+           "-L", LIB_DIR, "-leals_b200", "-Wl,-rpath,$ORIGIN"]
+    digest = _digest(deps, cmd)
+    if not force and _fresh(out, digest):
         return out
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", out,
-                    "-L", LIB_DIR, "-leals_b200", "-Wl,-rpath,$ORIGIN"], check=True)
+    subprocess.run(cmd, check=True)
+    _stamp(out, digest)
     return out
 
 
