@@ -344,25 +344,65 @@ eval_filter_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_consta
               for (int i = 0; i < kCols; i++) cnt[j] += (i < nvalid && v[i] > thr_hi) ? 1 : 0;
             }
           } else {
-            // Candidates: "may exceed the gt score" (flag 1) or "|score| may reach 1" (flag 2).  They are rare — 0.7
-            // per warp, tile and column half at 10M x 2M — so the loop is organised by COLUMN: two compares and
-            // one warp vote per column (uniform, no per-lane masks or prefix scans); a column somebody hits
-            // appends its pairs to this warp's shared-memory staging buffer (lane offsets from the vote), and the
-            // buffer goes to the global list with ONE atomic per flush.  (One atomic per pair made this pass
-            // 1.9 s of a 5 s evaluation; per-lane 64-bit masks + a scan per tile 61 ms; profiles r02b-r02m.)
-            const bool mine_live = slot[j] >= 0;
+            // candidate masks: bit i of m1 = "may exceed the gt score", of m2 = "|score| may reach 1".  Almost every
+            // lane has no candidate in a given tile (0.04 per lane and tile at 10M x 2M), so a two-compare screen
+            // per score comes first and the masks are only built by the lanes that need them.
+            uint32_t m1[2] = {0u, 0u}, m2[2] = {0u, 0u};
+            const float t_pos = fminf(thr_lo, thr_one), t_neg = -thr_one;
+            bool hit = false;
 #pragma unroll
-            for (int i = 0; i < kCols; i++) {
-              const bool c1 = v[i] >= thr_lo, c2 = fabsf(v[i]) >= thr_one;
-              const bool c = mine_live && (c1 || c2) && i < nvalid;
-              const unsigned bal = __ballot_sync(kFullMask, c);
-              if (bal) {
-                const int cntb = __popc(bal);
-                if (fill + cntb > C::kStagePairs) flush();
-                if (c) stage_buf[fill + __popc(bal & ((1u << lane) - 1u))] =
-                    EvalPair{slot[j], a.perm[it * kTN + hf * kCols + i], (c1 ? 1 : 0) | (c2 ? 2 : 0), 0};
-                fill += cntb;
+            for (int i = 0; i < kCols; i++) hit |= (v[i] >= t_pos) | (v[i] <= t_neg);
+            if (hit && slot[j] >= 0) {
+#pragma unroll
+              for (int c = 0; c < 2; c++) {
+                uint32_t b1 = 0, b2 = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                  b1 |= (v[c * 32 + i] >= thr_lo ? 1u : 0u) << i;
+                  b2 |= (fabsf(v[c * 32 + i]) >= thr_one ? 1u : 0u) << i;
+                }
+                const int lim = nvalid - c * 32;
+                const uint32_t live = lim <= 0 ? 0u : (lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u));
+                m1[c] = b1 & live;
+                m2[c] = b2 & live;
               }
+            }
+            // Warp-aggregated append into this warp's shared-memory staging buffer; the buffer goes to the global
+            // list with ONE atomic per flush (one atomic per pair — ~700 dependent atomics per thread — made this
+            // pass 1.9 s of a 5 s evaluation at 10M x 2M; one per warp and tile still 0.26 s: profiles r2d / r2e).
+            // Tried and dropped: one warp vote per COLUMN instead of per-lane masks + scan — 64 unrolled copies
+            // of the append path per user tile: 457 ms instead of 61 (r02n).
+            const int mine = __popc(m1[0] | m2[0]) + __popc(m1[1] | m2[1]);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int up = __shfl_up_sync(kFullMask, incl, o);
+              if (lane >= o) incl += up;
+            }
+            const int total = __shfl_sync(kFullMask, incl, 31);
+            if (total > 0) {
+              if (fill + total > C::kStagePairs) flush();
+              const bool direct = total > C::kStagePairs;          // more than the buffer holds: straight to the list
+              unsigned long long wbase = 0;
+              if (direct) {
+                if (lane == 0) wbase = atomicAdd(a.n_pairs, (unsigned long long)total);
+                wbase = __shfl_sync(kFullMask, wbase, 0);
+              }
+              int at = fill + incl - mine;
+#pragma unroll
+              for (int c = 0; c < 2; c++) {
+                uint32_t any = m1[c] | m2[c];
+                while (any) {
+                  const int i = __ffs(any) - 1;
+                  any &= any - 1;
+                  const int fl = ((m1[c] >> i) & 1) | (((m2[c] >> i) & 1) << 1);
+                  const EvalPair pr{slot[j], a.perm[it * kTN + hf * kCols + c * 32 + i], fl, 0};
+                  if (!direct) stage_buf[at] = pr;
+                  else if (wbase + (unsigned long long)(at - fill) < a.cap_pairs) a.pairs[wbase + (unsigned long long)(at - fill)] = pr;
+                  at++;
+                }
+              }
+              if (!direct) fill += total;
             }
           }
         }
