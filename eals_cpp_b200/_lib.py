@@ -61,6 +61,7 @@ SIGNATURES = {
     "eals_get_S": (C.c_int, [_P, C.c_int32, _P, _P]),
     "eals_update_user": (C.c_int, [_P]),
     "eals_update_item": (C.c_int, [_P]),
+    "eals_run_epochs": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "eals_sweep_users": (C.c_int, [_P]),
     "eals_sweep_items": (C.c_int, [_P]),
     "eals_gram_users": (C.c_int, [_P]),

@@ -232,6 +232,12 @@ struct eals_model {
   cudaStream_t side_stream = nullptr;   // routing of the final predictions runs here, under the Gram
   cudaEvent_t ev_swept = nullptr, ev_routed = nullptr;
   bool route_pending = false;
+  // whole epochs as one CUDA graph (eals_run_epochs): the launch-bound configurations (yelp-sized matrices:
+  // ~170 launches of a few microseconds each per epoch) replay a captured epoch instead of re-issuing it
+  cudaGraphExec_t epoch_graph = nullptr;
+  long long graph_key = -1, config_gen = 0;
+  long long graph_launches_per_epoch = 0;
+  bool capturing = false;
   int route_todo = 0;            // 1 / 2: the user / item sweep's staged predictions still have to be routed
   bool local_peers = false;      // peers are plain pointers of models in this process (eals_group), not CUDA IPC mappings
   bool pc_attached = false;      // caches usable: single rank, or both peers' cache sets mapped
@@ -867,6 +873,7 @@ int compute_item_weights(eals_model* m, int space, const int64_t* col_ptr_full) 
 
 int ensure_partials(eals_model* m, size_t n) {
   if (n <= m->partials_len) return EALS_OK;
+  if (m->capturing) return fail(EALS_ERR_STATE, "scratch would have to grow inside a captured epoch");
   cudaFree(m->partials);
   m->partials = nullptr;
   m->partials_len = 0;
@@ -900,12 +907,14 @@ void fold_timings(eals_model* m) {
 }
 
 void tic(eals_model* m, int which) {
+  if (m->capturing) return;      // no timing events inside a captured epoch
   if (m->pending[which].size() >= 2048) { cudaStreamSynchronize(m->stream); fold_timings(m); }
   cudaEvent_t e = take_event(m);
   cudaEventRecord(e, m->stream);
   m->pending[which].emplace_back(e, nullptr);
 }
 void toc(eals_model* m, int which) {
+  if (m->capturing) return;
   cudaEvent_t e = take_event(m);
   cudaEventRecord(e, m->stream);
   m->pending[which].back().second = e;
@@ -1903,6 +1912,7 @@ int eals_destroy(eals_model* m) {
   cudaFree(m->full_rp); cudaFree(m->full_cp); cudaFree(m->full_ci); cudaFree(m->full_ri); cudaFree(m->route_tmp);
   fold_timings(m);
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
+  if (m->epoch_graph) cudaGraphExecDestroy(m->epoch_graph);
   if (m->ev_blk0_a) { cudaEventDestroy(m->ev_blk0_a); cudaEventDestroy(m->ev_blk0_b); }
   if (m->side_stream) { cudaStreamSynchronize(m->side_stream); cudaStreamDestroy(m->side_stream); cudaEventDestroy(m->ev_swept); cudaEventDestroy(m->ev_routed); }
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -1989,6 +1999,7 @@ int eals_set_train(eals_model* m, int32_t input_space, const int64_t* row_ptr, c
   if (!m || !row_ptr || !col_idx || !col_ptr || !row_idx) return fail(EALS_ERR_ARG, "null argument");
   if ((row_val == nullptr) != (col_val == nullptr)) return fail(EALS_ERR_ARG, "row_val and col_val must both be given or both be null");
   CU(cudaSetDevice(m->p.device));
+  m->config_gen++;
   OK(build_side(m, m->users, m->ub, m->ue, m->N, input_space, row_ptr, col_idx, row_val));
   OK(build_side(m, m->items, m->ib, m->ie, m->M, input_space, col_ptr, row_idx, col_val));
   return build_pred_cache(m, input_space, row_ptr, col_idx, col_ptr, row_idx);
@@ -2204,6 +2215,65 @@ int eals_update_item(eals_model* m) {
   return eals_gram_items(m);
 }
 
+// n epochs (update_user + update_item each).  use_graph: the epoch is captured ONCE into a CUDA graph — after
+// one ordinary epoch, so that every scratch buffer has its final size and the symmetric prediction cache is in
+// its steady state — and replayed; the graph is dropped whenever the matrix, the stream or the cache state
+// changes.  Single-rank models only (between ranks the exchange is issued by the host layer).
+int eals_run_epochs(eals_model* m, int32_t n, int32_t use_graph) {
+  if (!m || n < 0) return fail(EALS_ERR_ARG, "bad argument");
+  if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised");
+  CU(cudaSetDevice(m->p.device));
+  const bool graph_ok = use_graph && m->n_ranks <= 1 && m->peersU.n == 0 && !(m->p.flags & EALS_FLAG_SYNC_EACH_CALL) &&
+                        m->pred_refresh_every == 0;
+  int done = 0;
+  if (graph_ok && n > 0) {
+    // steady state: both caches valid (or no cache at all) — reached after one ordinary epoch
+    const bool steady = !m->pcache_on || !m->pc_attached || (m->pc_u_valid && !m->pc_i_valid);
+    if (!steady || m->epoch_graph == nullptr || m->graph_key != m->config_gen) {
+      OK(eals_update_user(m)); OK(eals_update_item(m));      // ordinary epoch: sizes scratch, settles the cache state
+      done = 1;
+    }
+    if (done < n && (m->epoch_graph == nullptr || m->graph_key != m->config_gen)) {
+      if (m->epoch_graph) { cudaGraphExecDestroy(m->epoch_graph); m->epoch_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      // The legacy default stream (what a host that shares "the current stream" may have handed us) cannot be
+      // captured: record on the model's own stream; the finished graph is launched on m->stream all the same.
+      cudaStream_t user_stream = m->stream;
+      m->stream = m->own_stream;
+      const cudaError_t e0 = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+      if (e0 != cudaSuccess) {
+        m->stream = user_stream;
+        cudaGetLastError();
+        return fail(EALS_ERR_CUDA, "cudaStreamBeginCapture -> %s", cudaGetErrorString(e0));
+      }
+      m->capturing = true;
+      const long long launches_before = m->launches;
+      int rc = eals_update_user(m);
+      if (rc == EALS_OK) rc = eals_update_item(m);
+      m->capturing = false;
+      m->graph_launches_per_epoch = m->launches - launches_before;
+      m->launches = launches_before;      // captured, not executed
+      const cudaError_t e = cudaStreamEndCapture(m->stream, &g);
+      m->stream = user_stream;
+      if (e != cudaSuccess) cudaGetLastError();
+      if (rc != EALS_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) return fail(EALS_ERR_CUDA, "epoch capture -> %s", cudaGetErrorString(e));
+      const cudaError_t e2 = cudaGraphInstantiate(&m->epoch_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (e2 != cudaSuccess) return fail(EALS_ERR_CUDA, "epoch graph instantiation -> %s", cudaGetErrorString(e2));
+      m->graph_key = m->config_gen;
+      // the captured calls toggled the host-side cache flags exactly as an executed epoch would: still steady
+    }
+    for (; done < n; done++) {
+      CU(cudaGraphLaunch(m->epoch_graph, m->stream));
+      m->launches += m->graph_launches_per_epoch;
+    }
+    return EALS_OK;
+  }
+  for (; done < n; done++) { OK(eals_update_user(m)); OK(eals_update_item(m)); }
+  return EALS_OK;
+}
+
 int eals_update_user_row(eals_model* m, int32_t u) {
   if (!m) return fail(EALS_ERR_ARG, "null model");
   if (u < m->ub || u >= m->ue) return fail(EALS_ERR_ARG, "user %d not owned by this model", u);
@@ -2352,6 +2422,7 @@ int eals_set_stream(eals_model* m, void* cuda_stream, int32_t restore_own) {
   CU(cudaStreamSynchronize(m->stream));
   fold_timings(m);
   m->stream = restore_own ? m->own_stream : (cudaStream_t)cuda_stream;
+  m->config_gen++;
   return EALS_OK;
 }
 

@@ -166,6 +166,14 @@ int eals_get_S(eals_model* m, int32_t space, double* SU, double* SV);
 int eals_update_user(eals_model* m);
 int eals_update_item(eals_model* m);
 
+/* n epochs = n x (eals_update_user, eals_update_item).  With use_graph != 0 the epoch is captured once into a
+ * CUDA graph (after one ordinary epoch, so that scratch sizes and the symmetric prediction cache are in their
+ * steady state) and REPLAYED: the yelp-sized configurations are launch-bound — ~170 kernels of a few
+ * microseconds per epoch — and a replayed graph removes the per-launch cost.  Bit-identical to the ordinary
+ * calls (same kernels, same order).  The graph is rebuilt after eals_set_train / eals_set_stream; the phase
+ * timers do not advance during replayed epochs.  Single-rank models only (use_graph is ignored otherwise). */
+int eals_run_epochs(eals_model* m, int32_t n, int32_t use_graph);
+
 /* The two stages of the above, separately (for hosts that overlap the exchange). */
 int eals_sweep_users(eals_model* m);
 int eals_sweep_items(eals_model* m);

@@ -553,3 +553,40 @@ def test_tensor_core_filter_pair_overflow_falls_back_to_exact(monkeypatch):
     want = port.evaluate(gt, 10, compat=True)
     assert fals.eval_stats()["engine"] == "fp64"
     assert np.array_equal(got[4], want[4]) and np.array_equal(got[1], want[1])
+
+
+def test_epochs_replayed_as_a_cuda_graph_are_bit_identical(monkeypatch):
+    """eals_run_epochs(use_graph=1): one captured epoch replayed — same kernels in the same order, so U and V must
+    equal the ordinary update_user / update_item calls to the last bit; the graph is rebuilt after setTrain."""
+    from eals_cpp_b200.model import MF_fastALS, SparseMat
+    M, N, K = 2500, 80, 32
+    row_ptr, col_idx = _heavy_matrix(M, N, heavy_cols=[1, 9], heavy_len=1800, seed=3)     # warp rows + slab pipeline
+    row_ptr2, col_idx2 = _heavy_matrix(M, N, heavy_cols=[4, 5, 6], heavy_len=300, seed=4)   # + one-CTA rows
+    rows = [sorted(set(col_idx[row_ptr[u]:row_ptr[u + 1]]) | set(col_idx2[row_ptr2[u]:row_ptr2[u + 1]])) for u in range(M)]
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col_idx = np.concatenate([np.array(r, np.int32) for r in rows])
+    sm = SparseMat.from_csr(M, N, row_ptr, col_idx)
+    a = MF_fastALS(sm, None, factors=K, showLoss=False)
+    b = MF_fastALS(sm, None, factors=K, showLoss=False)
+    for _ in range(5):
+        a.update_user(); a.update_item()
+    launches0 = b.kernel_launches()
+    b.run_epochs(5, graph=True)
+    assert np.array_equal(a.U, b.U) and np.array_equal(a.V, b.V)
+    assert b.kernel_launches() > launches0
+    la, lb = a.loss(), b.loss()
+    assert la == lb
+    # a new matrix: the captured graph must not be replayed on stale pointers / sizes
+    sm2 = SparseMat.from_csr(M, N, row_ptr2, col_idx2)
+    a.setTrain(sm2); b.setTrain(sm2)
+    for _ in range(3):
+        a.update_user(); a.update_item()
+    b.run_epochs(3, graph=True)
+    assert np.array_equal(a.U, b.U) and np.array_equal(a.V, b.V)
+    # factors replaced from outside between graph runs: the cache state is re-settled by an ordinary epoch first
+    U, V = a.U * 0.5, a.V * 2.0
+    a.setUV(U, V); b.setUV(U, V)
+    for _ in range(2):
+        a.update_user(); a.update_item()
+    b.run_epochs(2, graph=True)
+    assert np.array_equal(a.U, b.U) and np.array_equal(a.V, b.V)
