@@ -572,8 +572,8 @@ class MF_fastALS:
         at its sorted position and, with ``patch_S`` (default), the S caches follow every row update
         (update_user_SU / update_item_SV, MF_fastALS.cpp:324-335, 409-422) as in the paper's incremental
         mode.  ``patch_S=False`` reproduces the reference's arithmetic (stale caches)."""
-        if self.world > 1:
-            raise NotImplementedError("updateModel drives single rows; use a single-GPU model")
+        if self.world > 1 and not (self.peer_store and patch_S):
+            raise NotImplementedError("updateModel on several ranks needs the peer-store exchange and patch_S=True")
         u, i = int(u), int(i)
         if not (0 <= u < self.userCount and 0 <= i < self.itemCount):
             raise IndexError("updateModel: (u, i) outside the matrix")
@@ -583,18 +583,31 @@ class MF_fastALS:
                        host(sm.row_val), host(sm.col_val))
         grown = insert_interaction(sm, u, i)              # trainMatrix.setValue(u, i, 1); W.setValue(u, i, w_new)
         if grown is not None:
-            self.setTrain(grown)
+            self.setTrain(grown)                            # every rank: same matrix, same (unchanged) ranges
         Wi = self.Wi
         if Wi[i] == 0.0:                                    # a new item: weight and its term in the SV cache
             Wi[i] = self.w0 / self.itemCount
             self.Wi = Wi                                    # uploads and rebuilds SV with the new weight
+        # Several ranks: the OWNER of the row runs the single-row kernel, which stores the new row into every
+        # replica over NVLink; after a barrier every rank reads the row from its own replica and patches its S cache.
+        own_u = self.user_bounds[self.rank] <= u < self.user_bounds[self.rank + 1]
+        own_i = self.item_bounds[self.rank] <= i < self.item_bounds[self.rank + 1]
+
+        def row_update(which, r, mine, fn):
+            old = self._factor_row(which, r) if patch_S else None
+            if mine:
+                fn(r)
+            if self.world > 1:
+                import torch.distributed as dist
+                self.sync()
+                dist.barrier(group=self.group)
+            return old
+
         for _ in range(int(maxIterOnline)):
-            old = self._factor_row(_lib.BUF_U, u) if patch_S else None
-            self.update_user_thread(u)
+            old = row_update(_lib.BUF_U, u, own_u, self.update_user_thread)
             if patch_S:
                 self.update_user_SU(old, self._factor_row(_lib.BUF_U, u))
-            old = self._factor_row(_lib.BUF_V, i) if patch_S else None
-            self.update_item_thread(i)
+            old = row_update(_lib.BUF_V, i, own_i, self.update_item_thread)
             if patch_S:
                 self.update_item_SV(i, old, self._factor_row(_lib.BUF_V, i))
 

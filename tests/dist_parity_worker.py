@@ -79,6 +79,26 @@ def main():
     assert np.abs(fals.V - port.V).max() < 1e-10, rank
     assert np.abs(fals.SU - port.SU).max() <= 1e-11 * np.abs(port.SU).max()
     assert fals.replicas_consistent(), rank
+    # online update on the sharded model (one process per GPU): the owner runs the row kernel, the new row reaches
+    # every replica through the kernel's peer stores, every rank patches its S caches
+    if fals.peer_store:
+        rows2 = [list(col_idx2[row_ptr2[r]:row_ptr2[r + 1]]) for r in range(M)]
+        uu, ii = 5, next(c for c in range(N) if c not in rows2[5])
+        port.SU = port.p.gram_plain(port.U); port.SV = port.p.gram_weighted(port.V, port.Wi)
+        fals.refresh_S()
+        fals.updateModel(uu, ii)
+        rows2[uu] = sorted(rows2[uu] + [ii])
+        rp3 = np.concatenate([[0], np.cumsum([len(r) for r in rows2])]).astype(np.int64)
+        ci3 = np.concatenate([np.array(r, np.int32) for r in rows2])
+        port.row_ptr, port.col_idx = rp3, ci3
+        port.col_ptr, port.row_idx, port.cval, _ = csr_to_csc(M, N, rp3, ci3, None)
+        for _ in range(10):
+            port.update_user(uu, uu + 1)
+            port.update_item(ii, ii + 1)
+        assert fals.replicas_consistent(), rank
+        assert np.abs(fals.U - port.U).max() < 1e-10 and np.abs(fals.V - port.V).max() < 1e-10, rank
+        assert np.abs(fals.SU - port.SU).max() <= 1e-10 * np.abs(port.SU).max(), rank
+        assert np.abs(fals.SV - port.SV).max() <= 1e-10 * np.abs(port.SV).max(), rank
     res = fals.evaluate()
     want = port.evaluate(gt, 10, compat=True)[0]
     assert np.allclose(res, want, rtol=0, atol=1e-12), (res, want)

@@ -165,7 +165,8 @@ def test_update_model_host_flow_with_a_mocked_library():
 
     class Fake(mdl.MF_fastALS):
         def __init__(self):                          # no library, no device
-            self.world, self.userCount, self.itemCount, self.w0 = 1, M, N, 10.0
+            self.world, self.rank, self.userCount, self.itemCount, self.w0 = 1, 0, M, N, 10.0
+            self.user_bounds, self.item_bounds = [0, M], [0, N]
             self.trainMatrix = mdl.SparseMat.from_csr(M, N, row_ptr, col_idx)
             self._wi = np.ones(N); self._wi[3] = 0.0
         Wi = property(lambda self: self._wi.copy(), lambda self, w: (calls.append(("Wi", w.copy())), setattr(self, "_wi", w)))
