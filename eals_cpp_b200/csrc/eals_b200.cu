@@ -113,6 +113,9 @@ int dev_reserve(T** p, size_t* cap, size_t n) {
   return EALS_OK;
 }
 
+// Where the receive area of the copy-engine exchange starts inside a prediction-cache allocation of n values.
+inline size_t recv_offset(int64_t n) { return ((size_t)n + 15) & ~(size_t)15; }
+
 // Buckets of owned rows by length.  Bucket 0 = empty rows (skipped: MF_fastALS.cpp:249,344).
 // 1..4: one warp per row (1/2/3/4 nonzeros per lane); 5..7: one CTA per row (4 warps x 2, 4 x 3,
 // 8 x 2 nonzeros per thread); 8: heavy rows, split into slabs.  The finer the buckets, the closer a
@@ -217,6 +220,18 @@ struct eals_model {
   uint32_t *route_src_u = nullptr, *route_dst_u = nullptr, *route_src_i = nullptr, *route_dst_i = nullptr;
   size_t cap_stage_u = 0, cap_stage_i = 0, cap_rsrc_u = 0, cap_rdst_u = 0, cap_rsrc_i = 0, cap_rdst_i = 0;
   bool routed = false;
+  // Copy-engine exchange of the staged predictions (multi-rank): pair_cnt[su][ri] = nonzeros whose user belongs to
+  // rank su and whose item to rank ri (every rank computes the whole table from the full index arrays).  A sender's
+  // staging array is already in destination order, i.e. segmented by destination rank; each segment is copied
+  // (cudaMemcpyAsync, peer-to-peer: no SM involved, runs under the Gram) into the receiver's RECEIVE area — the
+  // second half of the allocation that holds the receiver's prediction cache, so no extra mapping is needed — at the
+  // offset that belongs to this sender; before its next sweep the receiver unpacks the area into the cache through
+  // recv_idx (a stable partition of its nonzeros by source rank: the order every sender's segment arrives in).
+  long long pair_cnt[8][8] = {{0}};
+  uint32_t *recv_idx_u = nullptr, *recv_idx_i = nullptr;
+  size_t cap_recv_idx_u = 0, cap_recv_idx_i = 0;
+  bool copy_route = false;
+  bool unpack_u_pending = false, unpack_i_pending = false;
   // multi-rank: a prediction cache that had to grow is not freed while peers may still map it (CUDA IPC):
   // the old buffer waits here until eals_ipc_gc; ipc_gen counts such reallocations
   std::vector<void*> graveyard;
@@ -322,19 +337,44 @@ int ensure_partials(eals_model* m, size_t n);
 // (search in the offsets; neighbouring threads walk the same path), its user u = row_idx[q] and the
 // CSR position p of (u, i) — a search inside the SHORT row u instead of inside a column that may
 // hold millions of entries.  map_i[q] = p for the owned items, map_u[p] = q for the owned users.
+struct RankBounds {
+  int32_t user[9], item[9];
+  int n;                                    // ranks (<= 1: no table)
+};
+
 __global__ void build_maps_kernel(const int64_t* __restrict__ cp, const int32_t* __restrict__ ri, int N,
                                   const int64_t* __restrict__ rp, const int32_t* __restrict__ ci, int64_t nnz,
                                   int ub, int ue, int64_t rp_ub, uint32_t* __restrict__ map_u,
-                                  int ib, int ie, int64_t cp_ib, uint32_t* __restrict__ map_i, int* __restrict__ bad) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nnz) return;
-  int lo = 0, hi = N;                       // largest i with cp[i] <= q
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (cp[mid] <= q) lo = mid; else hi = mid;
+                                  int ib, int ie, int64_t cp_ib, uint32_t* __restrict__ map_i, int* __restrict__ bad,
+                                  RankBounds rb, unsigned long long* __restrict__ pair_cnt) {
+  __shared__ unsigned int hist[64];
+  if (rb.n > 1) {
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
   }
-  const int i = lo, u = ri[q];
-  const bool own_u = u >= ub && u < ue, own_i = i >= ib && i < ie;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int i = 0, u = 0;
+  bool own_u = false, own_i = false;
+  if (q < nnz) {
+    int lo = 0, hi = N;                     // largest i with cp[i] <= q
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cp[mid] <= q) lo = mid; else hi = mid;
+    }
+    i = lo; u = ri[q];
+    own_u = u >= ub && u < ue; own_i = i >= ib && i < ie;
+    if (rb.n > 1) {                         // (owner of the user, owner of the item) of this nonzero
+      int su = 0, si = 0;
+#pragma unroll
+      for (int t = 1; t < 8; t++) { su += (t < rb.n && u >= rb.user[t]) ? 1 : 0; si += (t < rb.n && i >= rb.item[t]) ? 1 : 0; }
+      atomicAdd(&hist[su * 8 + si], 1u);
+    }
+  }
+  if (rb.n > 1) {
+    __syncthreads();
+    if (threadIdx.x < 64 && hist[threadIdx.x]) atomicAdd(pair_cnt + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
+  }
+  if (q >= nnz) return;
   if (!own_u && !own_i) return;
   int64_t a = rp[u], b = rp[u + 1];
   while (b - a > 1) {
@@ -344,6 +384,26 @@ __global__ void build_maps_kernel(const int64_t* __restrict__ cp, const int32_t*
   if (!(b > a && ci[a] == i)) { atomicExch(bad, 1); return; }
   if (own_i) map_i[q - cp_ib] = (uint32_t)a;
   if (own_u) map_u[a - rp_ub] = (uint32_t)q;
+}
+
+// key[t] = rank that owns idx[t] (bounds[0..n]); val[t] = t
+__global__ void source_rank_kernel(const int32_t* __restrict__ idx, int64_t n, RankBounds rb, bool by_user,
+                                   uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int x = idx[t];
+  int r = 0;
+#pragma unroll
+  for (int k = 1; k < 8; k++) r += (k < rb.n && x >= (by_user ? rb.user[k] : rb.item[k])) ? 1 : 0;
+  key[t] = (uint32_t)r;
+  val[t] = (uint32_t)t;
+}
+
+// cache[recv_idx[k]] = recv[k]: the receive area (segments in source-rank order) into the prediction cache
+__global__ void __launch_bounds__(256)
+pc_unpack_kernel(const double* __restrict__ recv, const uint32_t* __restrict__ recv_idx, int64_t n, double* __restrict__ cache) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) cache[recv_idx[k]] = recv[k];
 }
 
 __global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz, int* __restrict__ bad) {
@@ -442,7 +502,15 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
       if (*p && n <= *cap) return EALS_OK;
       if (*p && m->n_ranks > 1) { m->graveyard.push_back(*p); *p = nullptr; *cap = 0; }
       m->ipc_gen++;
-      return dev_reserve(p, cap, n + n / 16);   // a little headroom: matrices of similar size keep the buffers
+      // a little headroom: matrices of similar size keep the buffers.  Several ranks: the allocation is the
+      // cache followed by the receive area of the copy-engine exchange (recv_offset() doubles further on)
+      const size_t want = n + n / 16;
+      if (!multi) return dev_reserve(p, cap, want);
+      cudaFree(*p);
+      *p = nullptr; *cap = 0;
+      CU(cudaMalloc((void**)p, sizeof(double) * (2 * (want + 16) + 16)));
+      *cap = want;
+      return EALS_OK;
     };
     OK(reserve_shared(&m->pc_u, &m->cap_pc_u, (size_t)nu));
     OK(reserve_shared(&m->pc_i, &m->cap_pc_i, (size_t)ni));
@@ -452,18 +520,31 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
   int* bad = m->flags + 14;
   CU(cudaMemsetAsync(bad, 0, sizeof(int), m->stream));
   CU(cudaMemsetAsync(m->map_u, 0xff, sizeof(uint32_t) * (size_t)nu, m->stream));   // unreached CSR entries stay invalid
+  RankBounds rb;
+  rb.n = multi ? m->n_ranks : 1;
+  for (int r = 0; r <= 8; r++) {
+    rb.user[r] = multi && r <= m->n_ranks ? m->p.user_bounds[r] : 0;
+    rb.item[r] = multi && r <= m->n_ranks ? m->p.item_bounds[r] : 0;
+  }
+  OK(ensure_partials(m, 64));
+  unsigned long long* d_pairs = reinterpret_cast<unsigned long long*>(m->partials);
+  CU(cudaMemsetAsync(d_pairs, 0, 64 * sizeof(unsigned long long), m->stream));
   {
     const int me_ = single ? 0 : m->rank;
     build_maps_kernel<<<(unsigned)((nnz_total + 255) / 256), 256, 0, m->stream>>>(
-        d_cp, d_ri, m->N, d_rp, d_ci, nnz_total, m->ub, m->ue, rp[me_], m->map_u, m->ib, m->ie, cp[me_], m->map_i, bad);
+        d_cp, d_ri, m->N, d_rp, d_ci, nnz_total, m->ub, m->ue, rp[me_], m->map_u, m->ib, m->ie, cp[me_], m->map_i, bad, rb, d_pairs);
     OK(check_launch(m));
   }
+  unsigned long long h_pairs[64];
+  CU(cudaMemcpyAsync(h_pairs, d_pairs, sizeof(h_pairs), cudaMemcpyDeviceToHost, m->stream));
   check_perm_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, m->stream>>>(m->map_u, nu, bad);
   OK(check_launch(m));
   int h_bad = 0;
   CU(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   CU(cudaStreamSynchronize(m->stream));
   if (h_bad) return fail(EALS_ERR_ARG, "the CSR and CSC arrays do not describe the same matrix");
+  for (int a = 0; a < 8; a++)
+    for (int b = 0; b < 8; b++) m->pair_cnt[a][b] = (long long)h_pairs[a * 8 + b];
   // destination tables; the own rank's entries are filled now, the peers' by eals_ipc_attach
   const int nr = single ? 1 : m->n_ranks, me = single ? 0 : m->rank;
   {   // the peers' mappings stay (their buffers only move when THEY report a new ipc generation)
@@ -486,6 +567,33 @@ int build_pred_cache(eals_model* m, int space, const int64_t* row_ptr, const int
     OK(build_routes(m, m->map_u, nu, &m->pc_stage_u, &m->cap_stage_u, &m->route_src_u, &m->cap_rsrc_u, &m->route_dst_u, &m->cap_rdst_u));
     OK(build_routes(m, m->map_i, ni, &m->pc_stage_i, &m->cap_stage_i, &m->route_src_i, &m->cap_rsrc_i, &m->route_dst_i, &m->cap_rdst_i));
     m->routed = true;
+    // receiver side of the copy-engine exchange: the order the senders' segments arrive in = this rank's nonzeros
+    // stably partitioned by the rank that owns the OTHER index (users of an item column ascend and a rank's
+    // users are one contiguous range, so every sender's values arrive in ascending position)
+    m->copy_route = !(getenv("EALS_ROUTE_COPY") && getenv("EALS_ROUTE_COPY")[0] == '0');
+    m->unpack_u_pending = m->unpack_i_pending = false;
+    if (m->copy_route) {
+      auto build_recv = [&](const Side& sd, bool by_user, uint32_t** out, size_t* cap, double* scratch_a, double* scratch_b) -> int {
+        const int64_t n = sd.nnz;
+        OK(dev_reserve(out, cap, (size_t)std::max<int64_t>(n, 1)));
+        if (n == 0) return EALS_OK;
+        uint32_t* key = reinterpret_cast<uint32_t*>(scratch_a);            // staging arrays are not live yet:
+        uint32_t* key_out = key + n;                                         // 8 n bytes each
+        uint32_t* val = reinterpret_cast<uint32_t*>(scratch_b);
+        source_rank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(sd.idx, n, rb, by_user, key, val);
+        OK(check_launch(m));
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key_out, val, *out, (int)n, 0, 3, m->stream);
+        OK(dev_reserve(&m->route_tmp, &m->cap_route_tmp, std::max<size_t>(tmp, 16)));
+        if (cub::DeviceRadixSort::SortPairs(m->route_tmp, tmp, key, key_out, val, *out, (int)n, 0, 3, m->stream) != cudaSuccess)
+          return fail(EALS_ERR_CUDA, "receive-order sort");
+        CU(cudaStreamSynchronize(m->stream));
+        return EALS_OK;
+      };
+      // item columns hold USER ids (source = owner of the user); user rows hold ITEM ids
+      OK(build_recv(m->items, true, &m->recv_idx_i, &m->cap_recv_idx_i, m->pc_stage_i, m->pc_i + recv_offset(ni)));
+      OK(build_recv(m->users, false, &m->recv_idx_u, &m->cap_recv_idx_u, m->pc_stage_u, m->pc_u + recv_offset(nu)));
+    }
     tm.lap("pred cache: routes");
   }
   m->pcache_on = true;
@@ -1056,9 +1164,29 @@ int launch_route(eals_model* m, bool on_side_stream) {
     CU(cudaStreamWaitEvent(m->side_stream, m->ev_swept, 0));
     rs = m->side_stream;
   }
-  const int grid = (int)std::min<int64_t>((s.nnz + 255) / 256, 4 * m->sm_count);
-  eals::pc_route_kernel<<<grid, 256, 0, rs>>>(user ? m->pc_stage_u : m->pc_stage_i, user ? m->route_dst_u : m->route_dst_i, s.nnz, out);
-  OK(check_launch(m));
+  if (m->copy_route) {
+    // One peer-to-peer copy per destination rank (copy engines: no SM, runs under the Gram kernel): my segment of
+    // the destination-ordered staging array -> my slot of the destination's receive area.
+    const int me = m->rank, nr = m->n_ranks;
+    const double* stage = user ? m->pc_stage_u : m->pc_stage_i;
+    long long seg = 0;
+    for (int r = 0; r < nr; r++) {
+      // user sweep: I am the user-owner `me`, destination = item-owner r; item sweep: I am the item-owner, dest = user-owner r
+      const long long cnt = user ? m->pair_cnt[me][r] : m->pair_cnt[r][me];
+      long long off = 0;                                       // senders before me in r's receive area
+      for (int q = 0; q < me; q++) off += user ? m->pair_cnt[q][r] : m->pair_cnt[r][q];
+      const long long dst_n = (long long)out.bound[r + 1] - (long long)out.bound[r];   // values in r's cache
+      if (cnt > 0)
+        CU(cudaMemcpyAsync(out.base[r] + recv_offset(dst_n) + off, stage + seg, sizeof(double) * (size_t)cnt, cudaMemcpyDefault, rs));
+      seg += cnt;
+    }
+    if (seg != s.nnz) return fail(EALS_ERR_STATE, "routing table does not cover the staged predictions (%lld of %lld)", seg, (long long)s.nnz);
+    (user ? m->unpack_i_pending : m->unpack_u_pending) = true;      // SPMD: every rank sweeps the same side now
+  } else {
+    const int grid = (int)std::min<int64_t>((s.nnz + 255) / 256, 4 * m->sm_count);
+    eals::pc_route_kernel<<<grid, 256, 0, rs>>>(user ? m->pc_stage_u : m->pc_stage_i, user ? m->route_dst_u : m->route_dst_i, s.nnz, out);
+    OK(check_launch(m));
+  }
   if (rs != m->stream) {
     CU(cudaEventRecord(m->ev_routed, m->side_stream));
     m->route_pending = true;
@@ -1077,9 +1205,28 @@ int join_route(eals_model* m) {
   return EALS_OK;
 }
 
+// Receive areas filled by the other ranks' copies (complete once the all-reduce after their sweep has completed,
+// which the host layer issues between the half-epochs) -> the prediction caches.
+int unpack_pending(eals_model* m) {
+  for (int side = 0; side < 2; side++) {
+    bool& pend = side == 0 ? m->unpack_u_pending : m->unpack_i_pending;
+    if (!pend) continue;
+    pend = false;
+    const bool valid = side == 0 ? m->pc_u_valid : m->pc_i_valid;
+    const int64_t n = side == 0 ? m->users.nnz : m->items.nnz;
+    if (!valid || n == 0) continue;
+    double* cache = side == 0 ? m->pc_u : m->pc_i;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 8 * m->sm_count);
+    pc_unpack_kernel<<<grid, 256, 0, m->stream>>>(cache + recv_offset(n), side == 0 ? m->recv_idx_u : m->recv_idx_i, n, cache);
+    OK(check_launch(m));
+  }
+  return EALS_OK;
+}
+
 int sweep(eals_model* m, bool user, int only_row) {
   if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised (eals_init_factors / eals_set_factors)");
   OK(join_route(m));
+  OK(unpack_pending(m));
   Side& s = user ? m->users : m->items;
   CdSide a;
   a.ptr = s.ptr; a.idx = s.idx; a.val = s.val;
@@ -1255,6 +1402,8 @@ int launch_loss_rows(eals_model* m, const eals::LossSide& a, Side& s, int* n_par
 int loss_terms_enqueue(eals_model* m) {
   if (!m->factors_set) return fail(EALS_ERR_STATE, "factors not initialised");
   CU(cudaSetDevice(m->p.device));
+  OK(join_route(m));
+  OK(unpack_pending(m));
   tic(m, T_LOSS);
   eals::LossSide a;
   Side& s = m->users;
@@ -1907,6 +2056,7 @@ int eals_destroy(eals_model* m) {
   cudaFree(m->pc_u); cudaFree(m->pc_i); cudaFree(m->map_u); cudaFree(m->map_i);
   cudaFree(m->pc_stage_u); cudaFree(m->pc_stage_i);
   cudaFree(m->route_src_u); cudaFree(m->route_dst_u); cudaFree(m->route_src_i); cudaFree(m->route_dst_i);
+  cudaFree(m->recv_idx_u); cudaFree(m->recv_idx_i);
   for (void* p : m->graveyard) cudaFree(p);
   if (m->eval) { m->eval->release(); delete m->eval; m->eval = nullptr; }
   cudaFree(m->full_rp); cudaFree(m->full_cp); cudaFree(m->full_ci); cudaFree(m->full_ri); cudaFree(m->route_tmp);
