@@ -400,10 +400,15 @@ __global__ void source_rank_kernel(const int32_t* __restrict__ idx, int64_t n, R
 }
 
 // cache[recv_idx[k]] = recv[k]: the receive area (segments in source-rank order) into the prediction cache
+// Slots [local_lo, local_hi) — the segment this rank sent to itself — are read straight from the sender-side
+// staging array instead (no copy for them: a same-device cudaMemcpyAsync is an SM kernel, and an SM kernel queues
+// behind the Gram's CTAs, which fill the register file).
 __global__ void __launch_bounds__(256)
-pc_unpack_kernel(const double* __restrict__ recv, const uint32_t* __restrict__ recv_idx, int64_t n, double* __restrict__ cache) {
+pc_unpack_kernel(const double* __restrict__ recv, const uint32_t* __restrict__ recv_idx, int64_t n, double* __restrict__ cache,
+                 const double* __restrict__ local_src, int64_t local_lo, int64_t local_hi) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) cache[recv_idx[k]] = recv[k];
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+    cache[recv_idx[k]] = (k >= local_lo && k < local_hi) ? local_src[k - local_lo] : recv[k];
 }
 
 __global__ void check_perm_kernel(const uint32_t* __restrict__ perm, int64_t nnz, int* __restrict__ bad) {
@@ -1176,7 +1181,7 @@ int launch_route(eals_model* m, bool on_side_stream) {
       long long off = 0;                                       // senders before me in r's receive area
       for (int q = 0; q < me; q++) off += user ? m->pair_cnt[q][r] : m->pair_cnt[r][q];
       const long long dst_n = (long long)out.bound[r + 1] - (long long)out.bound[r];   // values in r's cache
-      if (cnt > 0)
+      if (cnt > 0 && r != me)      // my own segment stays where it is: pc_unpack_kernel reads it from the staging array
         CU(cudaMemcpyAsync(out.base[r] + recv_offset(dst_n) + off, stage + seg, sizeof(double) * (size_t)cnt, cudaMemcpyDefault, rs));
       seg += cnt;
     }
@@ -1216,8 +1221,18 @@ int unpack_pending(eals_model* m) {
     const int64_t n = side == 0 ? m->users.nnz : m->items.nnz;
     if (!valid || n == 0) continue;
     double* cache = side == 0 ? m->pc_u : m->pc_i;
+    // my own segment: slot range in the receive order, and where it sits in the staging array of the side that sent it
+    const int me = m->rank;
+    long long lo = 0, src_off = 0;
+    for (int q = 0; q < me; q++) {
+      lo += side == 0 ? m->pair_cnt[me][q] : m->pair_cnt[q][me];        // senders before me in MY receive area
+      src_off += side == 0 ? m->pair_cnt[q][me] : m->pair_cnt[me][q];   // destinations before me in MY staging array
+    }
+    const long long cnt = m->pair_cnt[me][me];
+    const double* local_src = (side == 0 ? m->pc_stage_i : m->pc_stage_u) + src_off;   // pc_u is fed by the ITEM sweep's staging
     const int grid = (int)std::min<int64_t>((n + 255) / 256, 8 * m->sm_count);
-    pc_unpack_kernel<<<grid, 256, 0, m->stream>>>(cache + recv_offset(n), side == 0 ? m->recv_idx_u : m->recv_idx_i, n, cache);
+    pc_unpack_kernel<<<grid, 256, 0, m->stream>>>(cache + recv_offset(n), side == 0 ? m->recv_idx_u : m->recv_idx_i, n, cache,
+                                                  local_src, lo, lo + cnt);
     OK(check_launch(m));
   }
   return EALS_OK;
