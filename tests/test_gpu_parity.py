@@ -590,3 +590,31 @@ def test_epochs_replayed_as_a_cuda_graph_are_bit_identical(monkeypatch):
         a.update_user(); a.update_item()
     b.run_epochs(2, graph=True)
     assert np.array_equal(a.U, b.U) and np.array_equal(a.V, b.V)
+
+
+@pytest.mark.parametrize("shape", [(128, 50, 1, 1), (129, 128, 5, 10), (257, 129, 64, 3), (300, 1000, 16, 60), (640, 127, 33, 200)])
+def test_tensor_core_filter_edge_shapes(shape, monkeypatch):
+    """Edges of the tcgen05 evaluation: exactly / just over one 128-user tile, catalogues smaller than, equal to and
+    just over one 128-item tile, K = 1, K not a multiple of 16, topK larger than the catalogue — against the oracle
+    and the exact fp64 scan, per user."""
+    M, N, K, topK = shape
+    rng = np.random.default_rng(M + N + K)
+    row_ptr, col_idx = random_csr(M, N, max(2, min(10, N // 4)), seed=M + K)
+    fals, port = _models(M, N, row_ptr, col_idx, K)
+    fals.update_user(); port.update_user()
+    fals.update_item(); port.update_item()
+    gt = rng.integers(0, N, size=M).astype(np.int32)
+    for scale in (1.0, 25.0):
+        if scale != 1.0:
+            U = port.U * scale + rng.normal(0, 0.3, port.U.shape)
+            V = port.V * scale + rng.normal(0, 0.3, port.V.shape)
+            port.U[:], port.V[:] = U, V
+            fals.setUV(U, V)
+        for compat in (True, False):
+            want = port.evaluate(gt, topK, compat=compat)
+            monkeypatch.delenv("EALS_EVAL_SCALAR", raising=False)
+            got = fals.evaluate(gt, topK, exact=not compat, per_user=True)
+            assert fals.eval_stats()["engine"] == "tcgen05"
+            for k in range(1, 5):
+                assert np.array_equal(got[k], want[k]), (shape, scale, compat, k)
+            assert np.allclose(got[0], want[0], rtol=0, atol=1e-12)
