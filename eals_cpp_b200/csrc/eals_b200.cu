@@ -246,6 +246,10 @@ struct eals_model {
   int n_ranks = 1, rank = 0;
   cudaStream_t side_stream = nullptr;   // routing of the final predictions runs here, under the Gram
   cudaEvent_t ev_swept = nullptr, ev_routed = nullptr;
+  // two more streams for the peer-to-peer copies: several copy engines work at once (one stream serialises the
+  // 7 copies of an 8-GPU exchange; each is too small to fill NVLink on its own)
+  cudaStream_t copy_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   bool route_pending = false;
   // whole epochs as one CUDA graph (eals_run_epochs): the launch-bound configurations (yelp-sized matrices:
   // ~170 launches of a few microseconds each per epoch) replay a captured epoch instead of re-issuing it
@@ -1174,6 +1178,20 @@ int launch_route(eals_model* m, bool on_side_stream) {
     // the destination-ordered staging array -> my slot of the destination's receive area.
     const int me = m->rank, nr = m->n_ranks;
     const double* stage = user ? m->pc_stage_u : m->pc_stage_i;
+    // side stream + two helpers (round-robin over the destinations) when the copies run beside the Gram
+    cudaStream_t lanes[3] = {rs, rs, rs};
+    const bool fan = rs != m->stream && nr > 2;
+    if (fan) {
+      for (int c = 0; c < 2; c++) {
+        if (!m->copy_stream[c]) {
+          CU(cudaStreamCreateWithFlags(&m->copy_stream[c], cudaStreamNonBlocking));
+          CU(cudaEventCreateWithFlags(&m->ev_copied[c], cudaEventDisableTiming));
+        }
+        CU(cudaStreamWaitEvent(m->copy_stream[c], m->ev_swept, 0));
+        lanes[c + 1] = m->copy_stream[c];
+      }
+    }
+    int n_copy = 0;
     long long seg = 0;
     for (int r = 0; r < nr; r++) {
       // user sweep: I am the user-owner `me`, destination = item-owner r; item sweep: I am the item-owner, dest = user-owner r
@@ -1182,9 +1200,15 @@ int launch_route(eals_model* m, bool on_side_stream) {
       for (int q = 0; q < me; q++) off += user ? m->pair_cnt[q][r] : m->pair_cnt[r][q];
       const long long dst_n = (long long)out.bound[r + 1] - (long long)out.bound[r];   // values in r's cache
       if (cnt > 0 && r != me)      // my own segment stays where it is: pc_unpack_kernel reads it from the staging array
-        CU(cudaMemcpyAsync(out.base[r] + recv_offset(dst_n) + off, stage + seg, sizeof(double) * (size_t)cnt, cudaMemcpyDefault, rs));
+        CU(cudaMemcpyAsync(out.base[r] + recv_offset(dst_n) + off, stage + seg, sizeof(double) * (size_t)cnt, cudaMemcpyDefault,
+                           lanes[n_copy++ % 3]));
       seg += cnt;
     }
+    if (fan)                       // the helpers rejoin the side stream: ev_routed below covers all copies
+      for (int c = 0; c < 2; c++) {
+        CU(cudaEventRecord(m->ev_copied[c], m->copy_stream[c]));
+        CU(cudaStreamWaitEvent(m->side_stream, m->ev_copied[c], 0));
+      }
     if (seg != s.nnz) return fail(EALS_ERR_STATE, "routing table does not cover the staged predictions (%lld of %lld)", seg, (long long)s.nnz);
     (user ? m->unpack_i_pending : m->unpack_u_pending) = true;      // SPMD: every rank sweeps the same side now
   } else {
@@ -2079,6 +2103,8 @@ int eals_destroy(eals_model* m) {
   for (cudaEvent_t e : m->pool) cudaEventDestroy(e);
   if (m->epoch_graph) cudaGraphExecDestroy(m->epoch_graph);
   if (m->ev_blk0_a) { cudaEventDestroy(m->ev_blk0_a); cudaEventDestroy(m->ev_blk0_b); }
+  for (int c = 0; c < 2; c++)
+    if (m->copy_stream[c]) { cudaStreamSynchronize(m->copy_stream[c]); cudaStreamDestroy(m->copy_stream[c]); cudaEventDestroy(m->ev_copied[c]); }
   if (m->side_stream) { cudaStreamSynchronize(m->side_stream); cudaStreamDestroy(m->side_stream); cudaEventDestroy(m->ev_swept); cudaEventDestroy(m->ev_routed); }
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
