@@ -1180,7 +1180,8 @@ int launch_route(eals_model* m, bool on_side_stream) {
     const double* stage = user ? m->pc_stage_u : m->pc_stage_i;
     // side stream + two helpers (round-robin over the destinations) when the copies run beside the Gram
     cudaStream_t lanes[3] = {rs, rs, rs};
-    const bool fan = rs != m->stream && nr > 2;
+    static const bool no_fan = getenv("EALS_COPY_FAN") && getenv("EALS_COPY_FAN")[0] == '0';
+    const bool fan = rs != m->stream && nr > 2 && !no_fan;
     if (fan) {
       for (int c = 0; c < 2; c++) {
         if (!m->copy_stream[c]) {
