@@ -69,6 +69,7 @@ struct CdSide {
   double* pc_stage;        // nullptr: store directly through pc_map / pc_out
   int use_cache;           // 1: pc_in is valid on entry, read it instead of recomputing
   PeerSet peers;        // other ranks' replicas of X (n = 0: none)
+  int fence;            // 1: every thread ends with a system-scope fence when it may have stored to a peer (peers_release)
 };
 
 __device__ __forceinline__ void store_row_value(const CdSide& a, size_t off, double v) {
@@ -76,14 +77,15 @@ __device__ __forceinline__ void store_row_value(const CdSide& a, size_t off, dou
   for (int p = 0; p < a.peers.n; p++) a.peers.x[p][off] = v;
 }
 
-// Called by every thread of a sweep kernel after its last peer store: the stores are performed at
-// system scope before the thread exits, i.e. before the kernel counts as complete and the NCCL
-// all-reduce that orders them for the other ranks can start.  (Kernel completion should imply this; the
-// explicit fence costs one membar per thread per launch and removes the assumption.  One of five 8-GPU c4
-// runs of round 1 ended 0.19 % off in the loss after 8 epochs — not reproduced, cause not established;
-// profiles/README.md r01j.)
+// Optional (EALS_PEER_FENCE=1): every thread of a sweep kernel ends with a system-scope fence after its last
+// peer store.  Off by default: grid completion already performs the kernel's stores at system scope before
+// anything ordered after it in the stream (the event the other ranks wait on, or the NCCL all-reduce) can
+// start, and the fence is expensive — a CTA-per-row kernel cannot retire its CTA until the NVLink stores are
+// acknowledged: 129.0 -> 120.5 ms per epoch at 4 GPUs without it (profiles/r2/r02w_*), same loss bits, replicas
+// identical.  It was added in round 1 when one 8-GPU run ended 0.19 % off; that turned out to be the start-up
+// race (no barrier between init and the first peer store, fixed in round 2), not visibility.
 __device__ __forceinline__ void peers_release(const CdSide& a) {
-  if (a.peers.n > 0 || a.pc_out.n > 1) __threadfence_system();
+  if (a.fence && (a.peers.n > 0 || (a.pc_out.n > 1 && !a.pc_stage))) __threadfence_system();
 }
 
 // Store a prediction at global position g of the other orientation's cache (on whichever rank holds it).

@@ -1279,6 +1279,8 @@ int sweep(eals_model* m, bool user, int only_row) {
   a.reg = m->p.reg;
   a.pc_in = nullptr; a.pc_map = nullptr; a.pc_out = eals::PcOut{}; a.use_cache = 0; a.pc_stage = nullptr;
   a.peers = user ? m->peersU : m->peersV;
+  static const bool fence = getenv("EALS_PEER_FENCE") && getenv("EALS_PEER_FENCE")[0] == '1';
+  a.fence = fence ? 1 : 0;   // off by default: grid completion already orders the peer stores (cd_sweep.cuh, peers_release)
   if (only_row >= 0) {
     m->pc_u_valid = m->pc_i_valid = false;   // a single-row update changes factors behind the cache's back
     if (user) m->su_fresh = false;           // ... and U behind SU's back (MF_fastALS.cpp:243-322 never touches SU)
