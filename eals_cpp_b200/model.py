@@ -589,27 +589,38 @@ class MF_fastALS:
             Wi[i] = self.w0 / self.itemCount
             self.Wi = Wi                                    # uploads and rebuilds SV with the new weight
         # Several ranks: the OWNER of the row runs the single-row kernel, which stores the new row into every
-        # replica over NVLink; after a barrier every rank reads the row from its own replica and patches its S cache.
+        # replica over NVLink; after a barrier every rank reads the row from its own replica and patches its S
+        # caches.  The "old" row of a patch must be read BEFORE the owner's kernel can store into this replica: it is
+        # read once up front (barrier), and afterwards the row a rank read after step n is the old row of step n+1 —
+        # the owner's next store to it comes only after a barrier this rank joins after that read.  (Reading it at
+        # the top of every step raced with a faster owner: a zero patch on the slow rank, S caches apart.)
         own_u = self.user_bounds[self.rank] <= u < self.user_bounds[self.rank + 1]
         own_i = self.item_bounds[self.rank] <= i < self.item_bounds[self.rank + 1]
-
-        def row_update(which, r, mine, fn):
-            old = self._factor_row(which, r) if patch_S else None
-            if mine:
-                fn(r)
-            if self.world > 1:
-                import torch.distributed as dist
-                self.sync()
-                dist.barrier(group=self.group)
-            return old
-
+        old_u = self._factor_row(_lib.BUF_U, u) if patch_S else None
+        old_v = self._factor_row(_lib.BUF_V, i) if patch_S else None
+        self._rank_barrier()
         for _ in range(int(maxIterOnline)):
-            old = row_update(_lib.BUF_U, u, own_u, self.update_user_thread)
+            if own_u:
+                self.update_user_thread(u)
+            self._rank_barrier()
             if patch_S:
-                self.update_user_SU(old, self._factor_row(_lib.BUF_U, u))
-            old = row_update(_lib.BUF_V, i, own_i, self.update_item_thread)
+                new = self._factor_row(_lib.BUF_U, u)
+                self.update_user_SU(old_u, new)
+                old_u = new
+            if own_i:
+                self.update_item_thread(i)
+            self._rank_barrier()
             if patch_S:
-                self.update_item_SV(i, old, self._factor_row(_lib.BUF_V, i))
+                new = self._factor_row(_lib.BUF_V, i)
+                self.update_item_SV(i, old_v, new)
+                old_v = new
+
+    def _rank_barrier(self):
+        """Several processes: this rank's queued work is complete (its peer stores included) and every rank is here."""
+        if self.world > 1:
+            import torch.distributed as dist
+            self.sync()
+            dist.barrier(group=self.group)
 
     def runOneIteration(self):
         """One correct epoch (the reference's version leaves the S caches stale: :163-173)."""

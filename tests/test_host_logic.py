@@ -194,6 +194,51 @@ def test_update_model_host_flow_with_a_mocked_library():
         f.updateModel(M, 0)
 
 
+def test_update_model_on_two_ranks_reads_the_old_row_before_the_owner_stores():
+    """Sharded updateModel: the owner's single-row kernel stores the new row into EVERY replica.  A rank that is
+    slow to read the "old" row of its S patch must still see the row as it was before that store — two ranks as
+    threads over shared replicas, rank 1 late at every read; every patch on both ranks must be (k, k + 1)."""
+    import threading
+    import time
+    from eals_cpp_b200 import model as mdl
+    from eals_cpp_b200 import _lib
+    M, N = 8, 6
+    dense = np.ones((M, N), bool)                              # (u, i) already present: no setTrain
+    row_ptr, col_idx = _csr_of(dense)
+    rep = [{_lib.BUF_U: np.zeros(2), _lib.BUF_V: np.zeros(2)} for _ in range(2)]     # row u of U / row i of V per replica
+    barrier = threading.Barrier(2)
+
+    class FakeRank(mdl.MF_fastALS):
+        def __init__(self, rank):
+            self.world, self.rank, self.userCount, self.itemCount, self.w0 = 2, rank, M, N, 10.0
+            self.user_bounds, self.item_bounds, self.peer_store = [0, M // 2, M], [0, N // 2, N], True
+            self.trainMatrix = mdl.SparseMat.from_csr(M, N, row_ptr, col_idx)
+            self.patches = []
+        Wi = property(lambda self: np.ones(N))
+        def _factor_row(self, which, r):
+            if self.rank == 1:
+                time.sleep(0.01)                               # the late reader
+            return rep[self.rank][which].copy()
+        def _store_everywhere(self, which):
+            new = rep[self.rank][which] + 1.0
+            for r in rep:
+                r[which] = new.copy()
+        def update_user_thread(self, u): self._store_everywhere(_lib.BUF_U)
+        def update_item_thread(self, i): self._store_everywhere(_lib.BUF_V)
+        def update_user_SU(self, old, new): self.patches.append(("SU", old[0], new[0]))
+        def update_item_SV(self, i, old, new): self.patches.append(("SV", old[0], new[0]))
+        def _rank_barrier(self): barrier.wait(timeout=20)
+        def close(self): pass
+
+    ranks = [FakeRank(0), FakeRank(1)]                         # rank 0 owns user 1 and item 1
+    threads = [threading.Thread(target=f.updateModel, args=(1, 1)) for f in ranks]
+    for t in threads: t.start()
+    for t in threads: t.join(30)
+    want = [(kind, float(k), float(k + 1)) for k in range(10) for kind in ("SU", "SV")]
+    assert ranks[0].patches == want
+    assert ranks[1].patches == want
+
+
 def test_cost_partition_is_contiguous_complete_and_balances_cost():
     """eals_partition (used by eals_group and by the one-process-per-GPU path): bounds are monotone, cover every
     row, give every rank at least one row, and balance the per-row cost model rather than raw nonzeros."""
