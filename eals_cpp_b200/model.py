@@ -615,6 +615,14 @@ class MF_fastALS:
                 self.update_item_SV(i, old_v, new)
                 old_v = new
 
+    def barrier(self):
+        """Several processes: call on EVERY rank between raw host reads of a replica (``U``, ``V``, ``predict``,
+        ``_factor_row``) and the next sweep.  Those reads are local and not ordered against the other ranks: a rank
+        that is ahead starts its next sweep and stores finished rows into this replica while a slower rank is still
+        copying it out.  ``loss``, ``evaluate``, ``replicas_consistent``, ``setUV``, ``load`` and ``updateModel``
+        end in a collective and need nothing extra.  No-op on one rank."""
+        self._rank_barrier()
+
     def _rank_barrier(self):
         """Several processes: this rank's queued work is complete (its peer stores included) and every rank is here."""
         if self.world > 1:

@@ -49,6 +49,7 @@ def main():
     fals.update_item(); port.update_item()
     assert fals.replicas_consistent(), rank
     assert np.abs(fals.U - port.U).max() < 1e-10 and np.abs(fals.V - port.V).max() < 1e-10, rank
+    fals.barrier()        # raw replica reads are local: no rank may start the next sweep while another still reads
     for it in range(3):
         fals.update_user(); port.update_user()
         fals.update_item(); port.update_item()
