@@ -68,7 +68,8 @@ def test_port_reproduces_golden_run(port, name):
 
 
 @have_ref
-@pytest.mark.parametrize("K,M,N,dens,weighted", [(8, 120, 90, 6, False), (20, 200, 310, 15, True), (64, 90, 40, 12, False)])
+@pytest.mark.parametrize("K,M,N,dens,weighted", [(8, 120, 90, 6, False), (20, 200, 310, 15, True), (64, 90, 40, 12, False),
+                                                 (129, 70, 50, 9, False), (200, 60, 45, 8, True)])
 def test_port_matches_live_reference(port, K, M, N, dens, weighted):
     row_ptr, col_idx = random_csr(M, N, dens, seed=K * 7 + M, empty_frac=0.08)
     val = np.random.default_rng(K).uniform(0.5, 2.5, len(col_idx)) if weighted else None
