@@ -100,6 +100,24 @@ def test_port_matches_live_reference(port, K, M, N, dens, weighted):
 
 
 @have_ref
+def test_port_matches_live_reference_at_the_headline_size(port):
+    """BASELINE.json configs[0] in full (yelp-shaped: 25677 x 25815, 669k interactions, K = 64, the synthetic
+    stand-in bench.py calls c1): one whole epoch of the restatement against the reference's own object — factors,
+    S caches and loss bit for bit.  This is the size the CPU baseline of bench.py is quoted on."""
+    from eals_cpp_b200 import datasets
+    d = datasets.powerlaw_csr(**datasets.WORKLOADS["c1"])
+    K = datasets.WORKLOADS["c1"]["K"]
+    ref = Reference(d.M, d.N, d.row_ptr, d.col_idx, test_items=d.test_items, factors=K, topK=10)
+    m = PortModel(d.M, d.N, d.row_ptr, d.col_idx, factors=K, port=port)
+    assert np.array_equal(m.U, ref.U) and np.array_equal(m.V, ref.V) and np.array_equal(m.Wi, ref.Wi)
+    ref.update_user(); m.update_user()
+    assert np.array_equal(m.U, ref.U) and np.array_equal(m.SU, ref.SU)
+    ref.update_item(); m.update_item()
+    assert np.array_equal(m.V, ref.V) and np.array_equal(m.SV, ref.SV)
+    assert m.loss() == ref.loss()
+
+
+@have_ref
 def test_buildmodel_call_order_matches_our_sweep_drivers(port):
     """ref_harness's half-epoch drivers repeat buildModel()'s call order: the real buildModel()
     must land on the same factors."""
